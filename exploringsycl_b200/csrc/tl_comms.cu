@@ -1,0 +1,414 @@
+// tl_comms.cu -- the comms layer: replaces the reference's MPI layer (TeaLeaf/comms.c:7-82) for the
+// ranks of one NVSwitch-connected node, one process per GPU.
+//
+//   rendezvous / host scalars : a POSIX shared-memory segment named by the session string
+//   halo payloads             : pack kernels store straight into the neighbour's receive buffer
+//                               through CUDA-IPC peer mappings (NVLink stores), followed by a
+//                               release flag; the receiver's stream spins on the flag (acquire)
+//                               and unpacks.  No host staging, no MPI, no NCCL call on this path.
+//   host-buffer messages      : send_recv_message semantics of comms.c:31-52 through mailboxes in
+//                               the shared segment (the plugin-API path and the CPU tests).
+//
+// sum_over_ranks adds the per-rank values in rank order on every rank, so the result is
+// bit-identical on all ranks and from run to run (MPI_Allreduce's order is unspecified).
+#include <errno.h>
+#include <fcntl.h>
+#include <sched.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+#include <atomic>
+#include "tl_internal.h"
+
+#define TLC_MAX_RANKS TL_MAX_PEERS
+#define TLC_SLOT_DOUBLES (6 * 2 * 32776)
+#define TLC_MAGIC 0x7ea1eaf5u
+
+struct Mailbox {
+    std::atomic<unsigned long long> seq_w, seq_r;
+    int len;
+    int pad;
+    double data[TLC_SLOT_DOUBLES];
+};
+
+struct ShmHeader {
+    std::atomic<unsigned int> magic;
+    std::atomic<int> attached;
+    int num_ranks;
+    std::atomic<unsigned int> bar_count;
+    std::atomic<unsigned int> bar_gen;
+    double red[2][TLC_MAX_RANKS];
+    std::atomic<int> nb_list[TLC_MAX_RANKS][4]; // neighbour ranks each rank sends to (registered lazily)
+    // GPU arenas
+    cudaIpcMemHandle_t arena[TLC_MAX_RANKS];
+    unsigned long long arena_face_elems[TLC_MAX_RANKS];
+    int arena_device[TLC_MAX_RANKS];
+};
+
+struct tl_comms {
+    int rank, num_ranks, device, host_only;
+    char name[128];
+    size_t shm_bytes;
+    ShmHeader* hdr;
+    Mailbox* boxes; // [num_ranks][4][2]
+    unsigned int red_parity;
+    unsigned int bar_local_gen;
+    // GPU side (after attach)
+    double* arena;      // my device arena
+    size_t arena_bytes;
+    size_t face_elems;  // common (max over ranks) per-face capacity in doubles
+    void* peer_arena[TLC_MAX_RANKS];
+    unsigned long long xchg_seq; // exchange phases completed
+};
+
+static double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+static const double TLC_TIMEOUT_S = 120.0;
+
+#define SPIN_UNTIL(cond, what)                                              \
+    do {                                                                    \
+        double t0_ = now_s();                                               \
+        unsigned long spins_ = 0;                                           \
+        while (!(cond)) {                                                   \
+            if ((++spins_ & 0x3ff) == 0) {                                  \
+                sched_yield();                                              \
+                if (now_s() - t0_ > TLC_TIMEOUT_S) {                        \
+                    tl_set_error("comms timeout waiting for %s", what);     \
+                    return TL_ERR_COMMS;                                    \
+                }                                                           \
+            }                                                               \
+        }                                                                   \
+    } while (0)
+
+extern "C" int tl_comms_create(tl_comms** out, const char* session, int rank, int num_ranks, int device,
+                               int host_only)
+{
+    TL_CHECK_ARG(out && session && num_ranks >= 1 && num_ranks <= TLC_MAX_RANKS && rank >= 0 && rank < num_ranks,
+                 "bad arguments");
+    tl_comms* k = new tl_comms();
+    memset(k, 0, sizeof(*k));
+    k->rank = rank;
+    k->num_ranks = num_ranks;
+    k->device = device;
+    k->host_only = host_only;
+    snprintf(k->name, sizeof(k->name), "/tl_b200_%s", session);
+    k->shm_bytes = sizeof(ShmHeader) + sizeof(Mailbox) * (size_t)num_ranks * 4 * 2;
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(k->name);
+        fd = shm_open(k->name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)k->shm_bytes) != 0) {
+            tl_set_error("shm_open/ftruncate(%s) failed: %s", k->name, strerror(errno));
+            delete k;
+            return TL_ERR_COMMS;
+        }
+    } else {
+        double t0 = now_s();
+        for (;;) {
+            fd = shm_open(k->name, O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                if (fstat(fd, &st) == 0 && (size_t)st.st_size >= k->shm_bytes) break;
+                close(fd);
+                fd = -1;
+            }
+            if (now_s() - t0 > TLC_TIMEOUT_S) {
+                tl_set_error("timeout opening shm %s", k->name);
+                delete k;
+                return TL_ERR_COMMS;
+            }
+            usleep(1000);
+        }
+    }
+    void* m = mmap(nullptr, k->shm_bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) {
+        tl_set_error("mmap(%s) failed: %s", k->name, strerror(errno));
+        delete k;
+        return TL_ERR_COMMS;
+    }
+    k->hdr = (ShmHeader*)m;
+    k->boxes = (Mailbox*)((char*)m + sizeof(ShmHeader));
+    if (rank == 0) {
+        // ftruncate zero-fills; publish
+        k->hdr->num_ranks = num_ranks;
+        for (int r = 0; r < TLC_MAX_RANKS; ++r)
+            for (int i = 0; i < 4; ++i) k->hdr->nb_list[r][i].store(-1);
+        k->hdr->magic.store(TLC_MAGIC, std::memory_order_release);
+    } else {
+        SPIN_UNTIL(k->hdr->magic.load(std::memory_order_acquire) == TLC_MAGIC, "shm header");
+    }
+    k->hdr->attached.fetch_add(1);
+    SPIN_UNTIL(k->hdr->attached.load() >= num_ranks, "all ranks to attach");
+    *out = k;
+    return tl_comms_barrier(k);
+}
+
+extern "C" int tl_comms_destroy(tl_comms* k)
+{
+    if (!k) return TL_OK;
+    if (!k->host_only) {
+        for (int r = 0; r < k->num_ranks; ++r)
+            if (k->peer_arena[r] && r != k->rank) cudaIpcCloseMemHandle(k->peer_arena[r]);
+    }
+    tl_comms_barrier(k);
+    if (k->arena) cudaFree(k->arena);
+    munmap(k->hdr, k->shm_bytes);
+    if (k->rank == 0) shm_unlink(k->name);
+    delete k;
+    return TL_OK;
+}
+
+extern "C" int tl_comms_rank(const tl_comms* k) { return k ? k->rank : 0; }
+extern "C" int tl_comms_size(const tl_comms* k) { return k ? k->num_ranks : 1; }
+
+// barrier(), comms.c:73-76
+extern "C" int tl_comms_barrier(tl_comms* k)
+{
+    if (!k || k->num_ranks == 1) return TL_OK;
+    ShmHeader* h = k->hdr;
+    const unsigned int gen = h->bar_gen.load(std::memory_order_acquire);
+    if (h->bar_count.fetch_add(1, std::memory_order_acq_rel) == (unsigned int)(k->num_ranks - 1)) {
+        h->bar_count.store(0, std::memory_order_relaxed);
+        h->bar_gen.store(gen + 1, std::memory_order_release);
+    } else {
+        SPIN_UNTIL(h->bar_gen.load(std::memory_order_acquire) != gen, "barrier");
+    }
+    return TL_OK;
+}
+
+static int reduce_common(tl_comms* k, double* a, bool is_min)
+{
+    if (!k || k->num_ranks == 1) return TL_OK;
+    const unsigned int par = (k->red_parity++) & 1u;
+    k->hdr->red[par][k->rank] = *a;
+    std::atomic_thread_fence(std::memory_order_release);
+    TL_TRY(tl_comms_barrier(k));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    double v = k->hdr->red[par][0];
+    for (int r = 1; r < k->num_ranks; ++r) {
+        const double b = k->hdr->red[par][r];
+        if (is_min) v = (b < v) ? b : v;
+        else v += b; // rank order
+    }
+    *a = v;
+    return TL_OK;
+}
+// sum_over_ranks, comms.c:55-61
+extern "C" int tl_comms_sum(tl_comms* k, double* a) { return reduce_common(k, a, false); }
+// min_over_ranks, comms.c:64-70
+extern "C" int tl_comms_min(tl_comms* k, double* a) { return reduce_common(k, a, true); }
+
+static int nb_index(tl_comms* k, int src, int dst, bool create)
+{
+    for (int i = 0; i < 4; ++i) {
+        int v = k->hdr->nb_list[src][i].load(std::memory_order_acquire);
+        if (v == dst) return i;
+        if (v == -1) {
+            if (!create) return -1;
+            int expect = -1;
+            if (k->hdr->nb_list[src][i].compare_exchange_strong(expect, dst)) return i;
+            if (expect == dst) return i;
+        }
+    }
+    return -1;
+}
+
+// send_recv_message + wait_for_requests, comms.c:31-52, on host buffers.
+extern "C" int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double* recv_buffer, int buffer_len,
+                                  int neighbour, int send_tag, int recv_tag)
+{
+    TL_CHECK_ARG(k && send_buffer && recv_buffer && buffer_len >= 0 && buffer_len <= TLC_SLOT_DOUBLES &&
+                     neighbour >= 0 && neighbour < k->num_ranks && neighbour != k->rank &&
+                     (send_tag == 0 || send_tag == 1) && (recv_tag == 0 || recv_tag == 1), "bad arguments");
+    const int si = nb_index(k, k->rank, neighbour, true);
+    TL_CHECK_ARG(si >= 0, "more than 4 neighbours");
+    Mailbox* sb = &k->boxes[((size_t)k->rank * 4 + si) * 2 + send_tag];
+    SPIN_UNTIL(sb->seq_w.load(std::memory_order_acquire) == sb->seq_r.load(std::memory_order_acquire),
+               "mailbox to drain");
+    memcpy(sb->data, send_buffer, sizeof(double) * (size_t)buffer_len);
+    sb->len = buffer_len;
+    sb->seq_w.fetch_add(1, std::memory_order_release);
+    int ri = -1;
+    SPIN_UNTIL((ri = nb_index(k, neighbour, k->rank, false)) >= 0, "neighbour to post");
+    Mailbox* rb = &k->boxes[((size_t)neighbour * 4 + ri) * 2 + recv_tag];
+    SPIN_UNTIL(rb->seq_w.load(std::memory_order_acquire) > rb->seq_r.load(std::memory_order_acquire),
+               "message to arrive");
+    if (rb->len != buffer_len) {
+        tl_set_error("message length mismatch: expected %d got %d", buffer_len, rb->len);
+        return TL_ERR_COMMS;
+    }
+    memcpy(recv_buffer, rb->data, sizeof(double) * (size_t)buffer_len);
+    rb->seq_r.fetch_add(1, std::memory_order_release);
+    return TL_OK;
+}
+
+// initialise.c:34-134, for chunk == rank (one chunk per rank)
+extern "C" int tl_decompose(int grid_x_cells, int grid_y_cells, int num_chunks, int chunk, int* nx, int* ny,
+                            int* left, int* bottom, int neighbours[4], int* x_chunks_out, int* y_chunks_out)
+{
+    TL_CHECK_ARG(grid_x_cells > 0 && grid_y_cells > 0 && num_chunks >= 1 && chunk >= 0 && chunk < num_chunks,
+                 "bad arguments");
+    double best = 1.7976931348623157e308; // DBL_MAX
+    const double xc = (double)grid_x_cells, yc = (double)grid_y_cells;
+    int x_chunks = 0, y_chunks = 0;
+    for (int xx = 1; xx <= num_chunks; ++xx) {
+        if (num_chunks % xx) continue;
+        const int yy = num_chunks / xx;
+        if (num_chunks % yy) continue;
+        const double perimeter = ((xc / xx) * (xc / xx) + (yc / yy) * (yc / yy)) * 2;
+        const double area = (xc / xx) * (yc / yy);
+        const double metric = perimeter / area;
+        if (metric < best) {
+            x_chunks = xx;
+            y_chunks = yy;
+            best = metric;
+        }
+    }
+    if (!x_chunks || !y_chunks) {
+        tl_set_error("Failed to decompose the field with given parameters.");
+        return TL_ERR_ARG;
+    }
+    const int dx = grid_x_cells / x_chunks, dy = grid_y_cells / y_chunks;
+    const int mod_x = grid_x_cells % x_chunks, mod_y = grid_y_cells % y_chunks;
+    const int xx = chunk % x_chunks, yy = chunk / x_chunks;
+    const int add_x = (xx < mod_x), add_y = (yy < mod_y);
+    // remainder cells go to the first `mod` chunks of each axis (initialise.c:80-133)
+    const int add_x_prev = (xx < mod_x) ? xx : mod_x, add_y_prev = (yy < mod_y) ? yy : mod_y;
+    if (nx) *nx = dx + add_x;
+    if (ny) *ny = dy + add_y;
+    if (left) *left = xx * dx + add_x_prev;
+    if (bottom) *bottom = yy * dy + add_y_prev;
+    if (neighbours) {
+        neighbours[TL_FACE_LEFT] = (xx == 0) ? TL_EXTERNAL_FACE : chunk - 1;
+        neighbours[TL_FACE_RIGHT] = (xx == x_chunks - 1) ? TL_EXTERNAL_FACE : chunk + 1;
+        neighbours[TL_FACE_BOTTOM] = (yy == 0) ? TL_EXTERNAL_FACE : chunk - x_chunks;
+        neighbours[TL_FACE_TOP] = (yy == y_chunks - 1) ? TL_EXTERNAL_FACE : chunk + x_chunks;
+    }
+    if (x_chunks_out) *x_chunks_out = x_chunks;
+    if (y_chunks_out) *y_chunks_out = y_chunks;
+    return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPU peer path
+// ---------------------------------------------------------------------------------------------
+// Arena layout (identical on every rank, sized with the max face capacity over ranks):
+//   recv[face 0..3][parity 0..1][face_elems] doubles | flags[4] u64 | red slots [2][8] doubles | red flags [2][8] u64
+static size_t arena_recv_off(const tl_comms* k, int face, int parity)
+{
+    return ((size_t)face * 2 + parity) * k->face_elems;
+}
+static size_t arena_flags_off(const tl_comms* k) { return (size_t)8 * k->face_elems; }
+static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 4 + 2 * TL_MAX_PEERS * 2; }
+
+extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
+{
+    TL_CHECK_ARG(k && c, "null argument");
+    c->comms = k;
+    if (k->host_only || k->num_ranks == 1) return TL_OK;
+    TL_CUDA(cudaSetDevice(c->device));
+    ShmHeader* h = k->hdr;
+    h->arena_face_elems[k->rank] = c->face_elems;
+    h->arena_device[k->rank] = c->device;
+    TL_TRY(tl_comms_barrier(k));
+    size_t fe = 0;
+    for (int r = 0; r < k->num_ranks; ++r) fe = h->arena_face_elems[r] > fe ? h->arena_face_elems[r] : fe;
+    k->face_elems = fe;
+    k->arena_bytes = arena_total(k) * sizeof(double);
+    TL_CUDA(cudaMalloc((void**)&k->arena, k->arena_bytes));
+    TL_CUDA(cudaMemset(k->arena, 0, k->arena_bytes));
+    TL_CUDA(cudaDeviceSynchronize());
+    TL_CUDA(cudaIpcGetMemHandle(&h->arena[k->rank], k->arena));
+    std::atomic_thread_fence(std::memory_order_release);
+    TL_TRY(tl_comms_barrier(k));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    k->peer_arena[k->rank] = k->arena;
+    for (int f = 0; f < 4; ++f) {
+        const int n = c->nb[f];
+        if (n == TL_EXTERNAL_FACE || k->peer_arena[n]) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&k->peer_arena[n], h->arena[n], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            tl_set_error("cudaIpcOpenMemHandle(rank %d -> %d) failed: %s", k->rank, n, cudaGetErrorString(e));
+            return TL_ERR_COMMS;
+        }
+    }
+    static const int opposite[4] = {TL_FACE_RIGHT, TL_FACE_LEFT, TL_FACE_TOP, TL_FACE_BOTTOM};
+    for (int f = 0; f < 4; ++f) {
+        const int n = c->nb[f];
+        c->peers.nb_recv[f] = nullptr;
+        c->peers.nb_flag[f] = nullptr;
+        if (n == TL_EXTERNAL_FACE) continue;
+        double* base = (double*)k->peer_arena[n];
+        c->peers.nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
+        c->peers.nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
+    }
+    c->peers.rank = k->rank;
+    c->peers.num_ranks = k->num_ranks;
+    c->has_peers = true;
+    return tl_comms_barrier(k);
+}
+
+__global__ void k_signal(unsigned long long* remote_flag, unsigned long long v)
+{
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(v) : "memory");
+}
+
+__global__ void k_wait(unsigned long long* flag, unsigned long long v, DevScal* S)
+{
+    unsigned long long cur;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+        if (cur >= v) break;
+        if (clock64() - t0 > 40000000000LL) { // ~20 s: give up rather than hang the GPU
+            S->pad = 0xdeadu;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
+// remote_halo_driver.c:11-129 over NVLink: L/R fully completes (incl. unpack) before B/T packs.
+int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth)
+{
+    if (!k || k->num_ranks == 1) return TL_OK;
+    bool any_nb = false;
+    for (int f = 0; f < 4; ++f) any_nb |= (c->nb[f] != TL_EXTERNAL_FACE);
+    if (!any_nb) return TL_OK;
+    if (k->host_only || !c->has_peers) {
+        tl_set_error("halo exchange needs an attached GPU comms endpoint");
+        return TL_ERR_COMMS;
+    }
+    for (int phase = 0; phase < 2; ++phase) {
+        const int f0 = phase ? TL_FACE_BOTTOM : TL_FACE_LEFT;
+        const unsigned long long seq = ++k->xchg_seq;
+        const int par = (int)(seq & 1ull);
+        for (int f = f0; f < f0 + 2; ++f) {
+            if (c->nb[f] == TL_EXTERNAL_FACE) continue;
+            int len = 0;
+            TL_TRY(tlk_pack_face(c, fields, depth, f, true, c->peers.nb_recv[f] + (size_t)par * k->face_elems, &len));
+            k_signal<<<1, 1, 0, c->stream>>>(c->peers.nb_flag[f], seq);
+            ++g_tl_launches;
+        }
+        for (int f = f0; f < f0 + 2; ++f) {
+            if (c->nb[f] == TL_EXTERNAL_FACE) continue;
+            unsigned long long* my_flag = (unsigned long long*)(k->arena + arena_flags_off(k)) + f;
+            k_wait<<<1, 1, 0, c->stream>>>(my_flag, seq, c->scal);
+            ++g_tl_launches;
+            int len = 0;
+            TL_TRY(tlk_pack_face(c, fields, depth, f, false, k->arena + arena_recv_off(k, f, par), &len));
+        }
+        TL_CUDA(cudaGetLastError());
+    }
+    return TL_OK;
+}

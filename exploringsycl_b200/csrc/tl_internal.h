@@ -1,0 +1,143 @@
+// tl_internal.h -- internal types of the B200 TeaLeaf backend (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include "../../include/tealeaf_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout of a field (see DESIGN.md "Data layout"):
+//   element (jj,kk) lives at  base[off + jj*pitch + kk],  jj in [0,y), kk in [0,x)
+//   pitch is a multiple of 16 doubles (128 B) and `off` is chosen so that the first interior
+//   column (kk == hd) of every row starts a 128-byte line.  All fields of a chunk share
+//   (pitch, off), so one flat index addresses the same cell in every field.
+//   The allocation has `off` doubles of lead pad and >= 32 doubles of tail pad: 16-byte vector
+//   accesses that straddle a row end stay inside the allocation.
+// ---------------------------------------------------------------------------------------------
+struct Geo {
+    int x, y, hd;   // logical dims incl. halo, halo depth
+    int pitch, off; // row pitch and lead offset, in doubles
+};
+
+#define TL_TPB 128          // threads per CTA of the streaming kernels
+#define TL_TILE_COLS 256    // 2 cells per thread
+#define TL_MAX_PEERS 8
+
+// Device-resident solver scalars (one per chunk). Written by the tail CTA of the reduction
+// kernels, read by the head of the next kernel: alpha/beta never visit the host inside a solve.
+struct DevScal {
+    double rro, pw, rrn, alpha, beta, error, bb, eps;
+    double sums[8];
+    int iters;         // CG iterations completed in this solve
+    int conv;          // set when sqrt(|rrn|) < eps (cg_driver.c:24)
+    int p_pending;     // calc_ur ran: the matching calc_p must still run
+    int max_iters;
+    int conv_mode;     // 0: sqrt(|rrn|) < eps (cg_driver.c:24); 1: |rrn| < eps (cheby_driver.c:70)
+    unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
+    unsigned int seq;        // reduction sequence number (multi-GPU slot parity)
+    unsigned int pad;
+};
+
+// Peer tables for the NVLink path (filled by tl_comms_attach_chunk).
+struct PeerTable {
+    int rank, num_ranks;
+    // scalar all-reduce slots: slots[parity][src_rank] on every rank; peers write, owner reads.
+    double* slot_base[TL_MAX_PEERS];            // peer-mapped pointer to rank r's slot array
+    unsigned long long* flag_base[TL_MAX_PEERS]; // peer-mapped pointer to rank r's flag array
+    // halo staging: recv buffers of the 4 neighbours (peer-mapped), indexed by my face
+    double* nb_recv[4];
+    unsigned long long* nb_flag[4];
+};
+
+struct tl_chunk {
+    int device;
+    Geo g;
+    int nx, ny;
+    int max_iters;
+    int nb[4];
+    int left, bottom;
+    size_t field_elems;           // allocated doubles per 2-D field
+    double* f[TL_NUM_FIELDS];     // device
+    double *cell_x, *cell_y, *vertex_x, *vertex_y; // device 1-D
+    double* partials;             // device, per-tile partial sums (4 lanes)
+    int partial_cap;              // tiles
+    DevScal* scal;                // device
+    DevScal* scal_h;              // pinned host mirror [0] + two polling snapshots [1],[2]
+    double* d_alphas;             // device cg_alphas / cg_betas written by the resident loop
+    double* d_betas;
+    double* d_cheby;              // device copy of cheby alphas/betas (2*max_iters)
+    double *cg_alphas, *cg_betas, *cheby_alphas, *cheby_betas; // host (reference host reads/writes)
+    double* face_send[4];         // device staging, 6 fields * hd * max(x,y)
+    double* face_recv[4];
+    unsigned long long* face_flags; // device: arrival counters per face [4] (+ scalar flags)
+    double* red_slots;            // device: [2][TL_MAX_PEERS] all-reduce slots
+    unsigned long long* red_flags;// device: [2][TL_MAX_PEERS]
+    size_t face_elems;
+    double* h_stage;              // pinned host staging for the host-buffer pack/unpack API
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    tl_comms* comms;              // non-null once attached
+    PeerTable peers;
+    bool has_peers;
+    int resident_iters;           // CG iterations enqueued so far in the current solve (host bookkeeping)
+};
+
+// error handling ------------------------------------------------------------------------------
+void tl_set_error(const char* fmt, ...);
+int tl_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define TL_CUDA(call)                                                         \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return tl_cuda_fail(e_, #call, __FILE__, __LINE__); \
+    } while (0)
+#define TL_CHECK_ARG(cond, msg)                       \
+    do {                                              \
+        if (!(cond)) {                                \
+            tl_set_error("%s: %s", __func__, msg);    \
+            return TL_ERR_ARG;                        \
+        }                                             \
+    } while (0)
+#define TL_TRY(call)                 \
+    do {                             \
+        int rc_ = (call);            \
+        if (rc_) return rc_;         \
+    } while (0)
+
+extern long g_tl_launches;
+
+// kernel launchers (tl_kernels.cu) --------------------------------------------------------------
+// Scalar sources for the solver kernels: either an immediate (host-driven plugin API) or the
+// device-resident DevScal (resident loop).
+enum ScalMode { SCAL_IMM = 0, SCAL_DEV = 1 };
+// Reduction destinations inside DevScal for the tail CTA
+enum RedKind { RED_PW = 0, RED_RRN, RED_RRO_INIT, RED_NORM, RED_JACOBI, RED_SUMMARY, RED_BB };
+
+int tlk_set_chunk_data(tl_chunk* c, double x_min, double y_min, double dx, double dy);
+int tlk_set_initial_state(tl_chunk* c, double energy, double density);
+int tlk_set_state(tl_chunk* c, const tl_state* s);
+int tlk_copy_field(tl_chunk* c, int dst, int src, bool interior_only);
+int tlk_field_summary(tl_chunk* c);                       // -> scal->sums[0..3]
+int tlk_local_halos(tl_chunk* c, const int fields[6], int depth);
+int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len);
+int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev);                // -> scal->pw (& alpha when SCAL_DEV)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev); // -> scal->rrn (& beta, conv when SCAL_DEV)
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo);
+int tlk_cg_calc_pw(tl_chunk* c, bool first, bool rev);                 // fused p-update + matvec (SCAL_DEV only)
+int tlk_cheby_init(tl_chunk* c, double theta);
+int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
+int tlk_cheby_calc_u(tl_chunk* c);
+int tlk_ppcg_init(tl_chunk* c, double theta);
+int tlk_ppcg_calc_ur(tl_chunk* c);
+int tlk_ppcg_calc_sd(tl_chunk* c, double alpha, double beta);
+int tlk_jacobi_init(tl_chunk* c, int coefficient, double rx, double ry);
+int tlk_jacobi_iterate(tl_chunk* c);                      // -> scal->sums[0]
+int tlk_calculate_residual(tl_chunk* c);
+int tlk_calculate_2norm(tl_chunk* c, int field);          // -> scal->sums[0]
+int tlk_finalise(tl_chunk* c);
+int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters);
+int tlk_seed_rro(tl_chunk* c);                            // scal->rro = scal->sums[0] (after cg_init)
+
+// fetch the DevScal to the pinned mirror and wait
+int tl_fetch_scal(tl_chunk* c);

@@ -1,0 +1,874 @@
+// tl_kernels.cu -- sm_100a CUDA kernels of the TeaLeaf backend.
+//
+// Every kernel cites the reference kernel whose arithmetic it reproduces
+// (paths relative to /root/reference/TeaLeaf/c_kernels/sycl/).  Compiled with -fmad=false:
+// each fp64 operation is rounded exactly as the reference expression writes it, so all
+// element-wise results are bit-identical to the CPU oracle.  Reductions are deterministic
+// (fixed per-thread order -> xor-butterfly -> fixed-order sum of per-tile partials by the
+// last CTA to finish), single pass: no second launch, no host round trip.
+//
+// None of this is GEMM-shaped: the path is HBM-bound (0.22 flop/B), so the design rules are
+// coalesced 128-bit accesses on 128-byte-aligned rows, enough independent loads in flight,
+// and the minimum number of passes over HBM.  Tensor cores / TMEM are not used.
+#include "tl_internal.h"
+
+long g_tl_launches = 0;
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld2_ro(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ void st_pair(double* p, double2 v, bool v1)
+{
+    if (v1) st2(p, v);
+    else p[0] = v.x;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct RedArgs {
+    double* partials; // [NR][cap]
+    int cap;
+    DevScal* S;
+};
+
+// Deterministic single-pass grid reduction.  Every CTA writes its NR tile partials; the CTA that
+// takes the last ticket sums all tile partials in a fixed order.  Returns true in thread 0 of
+// that last CTA with the totals in `tot`.
+template <int NR>
+__device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
+                                            double (&tot)[NR])
+{
+    __shared__ double sm[NR][TL_TPB / 32];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double v = warp_sum(acc[r]);
+        if (lane == 0) sm[r][wid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double v = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
+            __stcg(&ra.partials[(size_t)r * ra.cap + tile], v);
+        }
+        __threadfence();
+        unsigned int t = atomicAdd(&ra.S->counter[0], 1u);
+        s_last = (t == (unsigned int)(ntiles - 1));
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const double* src = ra.partials + (size_t)r * ra.cap;
+        double s = 0.0;
+#pragma unroll 8
+        for (int k = tid; k < ntiles; k += TL_TPB) s += __ldcg(src + k);
+        s = warp_sum(s);
+        __syncthreads();
+        if (lane == 0) sm[r][wid] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) tot[r] = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
+        ra.S->counter[0] = 0u;
+        return true;
+    }
+    return false;
+}
+
+// shared.h:59-63 -- the reference SMVP association, spelled out on registers:
+//   (1 + (kx[i+1]+kx[i]) + (ky[i+x]+ky[i]))*a[i] - (kx[i+1]*a[i+1]+kx[i]*a[i-1]) - (ky[i+x]*a[i+x]+ky[i]*a[i-x])
+__device__ __forceinline__ double smvp(double kx0, double kx1, double ky0, double ky1, double a,
+                                       double al, double ar, double ad, double au)
+{
+    return (1.0 + (kx1 + kx0) + (ky1 + ky0)) * a - (kx1 * ar + kx0 * al) - (ky1 * au + ky0 * ad);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic row-tiled kernel: one thread per column, `rows` rows per CTA, optional NR-wide reduction.
+// Used for the setup / once-per-timestep kernels.  F: (long i, int jj, int kk, double* acc).
+// Fin: (const double* totals, DevScal* S) run by one thread after the grid reduction.
+// ---------------------------------------------------------------------------------------------
+template <int NR, class F, class Fin>
+__global__ void __launch_bounds__(TL_TPB) k_generic(Geo g, int k_lo, int k_hi, int j_lo, int j_hi, int rows,
+                                                    F f, Fin fin, RedArgs ra)
+{
+    const int kk = k_lo + blockIdx.x * TL_TPB + threadIdx.x;
+    const int j0 = j_lo + blockIdx.y * rows;
+    const int j1 = min(j0 + rows, j_hi);
+    double acc[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) acc[r] = 0.0;
+    if (kk < k_hi) {
+        long i = (long)g.off + (long)j0 * g.pitch + kk;
+        for (int jj = j0; jj < j1; ++jj, i += g.pitch) f(i, jj, kk, acc);
+    }
+    if constexpr (NR > 0) {
+        double tot[NR > 0 ? NR : 1];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        if (grid_reduce<(NR > 0 ? NR : 1)>(acc, ra, tile, gridDim.x * gridDim.y, tot)) fin(tot, ra.S);
+    }
+}
+
+struct NoFin {
+    __device__ void operator()(const double*, DevScal*) const {}
+};
+
+template <int NR, class F, class Fin>
+static int launch_generic(tl_chunk* c, int k_lo, int k_hi, int j_lo, int j_hi, F f, Fin fin)
+{
+    if (k_hi <= k_lo || j_hi <= j_lo) return TL_OK;
+    const int rows = 8;
+    dim3 grid((k_hi - k_lo + TL_TPB - 1) / TL_TPB, (j_hi - j_lo + rows - 1) / rows);
+    if (NR > 0 && (long)grid.x * grid.y > c->partial_cap) {
+        tl_set_error("partials capacity exceeded");
+        return TL_ERR_ARG;
+    }
+    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    k_generic<NR, F, Fin><<<grid, TL_TPB, 0, c->stream>>>(c->g, k_lo, k_hi, j_lo, j_hi, rows, f, fin, ra);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+#define INTERIOR_RANGE(c) (c)->g.hd, (c)->g.x - (c)->g.hd, (c)->g.hd, (c)->g.y - (c)->g.hd
+#define ALL_RANGE(c) 0, (c)->g.x, 0, (c)->g.y
+
+// ---------------------------------------------------------------------------------------------
+// Setup kernels
+// ---------------------------------------------------------------------------------------------
+// set_chunk_data.cpp:8-28
+__global__ void k_vertices(int x, int y, int hd, double x_min, double y_min, double dx, double dy,
+                           double* vertex_x, double* vertex_y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < x + 1) vertex_x[i] = x_min + dx * ((double)i - (double)hd);
+    if (i < y + 1) vertex_y[i] = y_min + dy * ((double)i - (double)hd);
+}
+// set_chunk_data.cpp:31-64 (cell centres)
+__global__ void k_cells(int x, int y, const double* vertex_x, const double* vertex_y, double* cell_x,
+                        double* cell_y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < x) cell_x[i] = 0.5 * (vertex_x[i] + vertex_x[i + 1]);
+    if (i < y) cell_y[i] = 0.5 * (vertex_y[i] + vertex_y[i + 1]);
+}
+
+int tlk_set_chunk_data(tl_chunk* c, double x_min, double y_min, double dx, double dy)
+{
+    const int n = max(c->g.x, c->g.y) + 1;
+    k_vertices<<<(n + 127) / 128, 128, 0, c->stream>>>(c->g.x, c->g.y, c->g.hd, x_min, y_min, dx, dy,
+                                                      c->vertex_x, c->vertex_y);
+    k_cells<<<(n + 127) / 128, 128, 0, c->stream>>>(c->g.x, c->g.y, c->vertex_x, c->vertex_y, c->cell_x,
+                                                   c->cell_y);
+    g_tl_launches += 2;
+    TL_CUDA(cudaGetLastError());
+    double* volume = c->f[TL_FIELD_VOLUME];
+    const double v = dx * dy; // set_chunk_data.cpp:54
+    return launch_generic<0>(c, ALL_RANGE(c),
+                             [=] __device__(long i, int, int, double*) { volume[i] = v; }, NoFin());
+}
+
+// set_chunk_state.cpp:8-27
+int tlk_set_initial_state(tl_chunk* c, double energy, double density)
+{
+    double* e0 = c->f[TL_FIELD_ENERGY0];
+    double* d = c->f[TL_FIELD_DENSITY];
+    return launch_generic<0>(c, ALL_RANGE(c),
+                             [=] __device__(long i, int, int, double*) {
+                                 e0[i] = energy;
+                                 d[i] = density;
+                             },
+                             NoFin());
+}
+
+// set_chunk_state.cpp:30-92
+int tlk_set_state(tl_chunk* c, const tl_state* sp)
+{
+    const tl_state s = *sp;
+    double* e0 = c->f[TL_FIELD_ENERGY0];
+    double* d = c->f[TL_FIELD_DENSITY];
+    double* u = c->f[TL_FIELD_U];
+    const double *cx = c->cell_x, *cy = c->cell_y, *vx = c->vertex_x, *vy = c->vertex_y;
+    const int x = c->g.x, y = c->g.y;
+    return launch_generic<0>(
+        c, ALL_RANGE(c),
+        [=] __device__(long i, int jj, int kk, double*) {
+            bool apply = false;
+            if (s.geometry == TL_GEOM_RECTANGULAR) {
+                apply = (vx[kk + 1] >= s.x_min && vx[kk] < s.x_max && vy[jj + 1] >= s.y_min &&
+                         vy[jj] < s.y_max);
+            } else if (s.geometry == TL_GEOM_CIRCULAR) {
+                double radius = sqrt((cx[kk] - s.x_min) * (cx[kk] - s.x_min) +
+                                     (cy[jj] - s.y_min) * (cy[jj] - s.y_min));
+                apply = (radius <= s.radius);
+            } else if (s.geometry == TL_GEOM_POINT) {
+                apply = (vx[kk] == s.x_min && vy[jj] == s.y_min);
+            }
+            if (apply) {
+                e0[i] = s.energy;
+                d[i] = s.density;
+            }
+            if (kk > 0 && kk < x - 1 && jj > 0 && jj < y - 1) u[i] = e0[i] * d[i];
+        },
+        NoFin());
+}
+
+// store_energy.cpp:6-24 (all cells), solver_methods.cpp:7-31 copy_u (interior), jacobi.cpp:120-137
+int tlk_copy_field(tl_chunk* c, int dst, int src, bool interior_only)
+{
+    double* D = c->f[dst];
+    const double* S = c->f[src];
+    auto f = [=] __device__(long i, int, int, double*) { D[i] = S[i]; };
+    if (interior_only) return launch_generic<0>(c, INTERIOR_RANGE(c), f, NoFin());
+    return launch_generic<0>(c, ALL_RANGE(c), f, NoFin());
+}
+
+// field_summary.cpp:6-151
+int tlk_field_summary(tl_chunk* c)
+{
+    const double *vol = c->f[TL_FIELD_VOLUME], *den = c->f[TL_FIELD_DENSITY], *e0 = c->f[TL_FIELD_ENERGY0],
+                 *u = c->f[TL_FIELD_U];
+    return launch_generic<4>(
+        c, INTERIOR_RANGE(c),
+        [=] __device__(long i, int, int, double* acc) {
+            const double cv = vol[i];
+            const double cm = cv * den[i];
+            acc[0] += cv;
+            acc[1] += cm;
+            acc[2] += cm * e0[i];
+            acc[3] += cm * u[i];
+        },
+        [=] __device__(const double* t, DevScal* S) {
+            S->sums[0] = t[0];
+            S->sums[1] = t[1];
+            S->sums[2] = t[2];
+            S->sums[3] = t[3];
+        });
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo kernels
+// ---------------------------------------------------------------------------------------------
+struct FieldList {
+    double* f[TL_NUM_EXCHANGE_FIELDS];
+    int n;
+};
+
+// local_halos.cpp:7-54 (update_left / update_right): every row jj in [0,y), `depth` layers.
+__global__ void k_halo_lr(Geo g, FieldList fl, int depth, int do_left, int do_right)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int jj = t / depth, d = t % depth;
+    if (jj >= g.y) return;
+    double* a = fl.f[blockIdx.y];
+    const long row = (long)g.off + (long)jj * g.pitch;
+    if (do_left) a[row + g.hd - 1 - d] = a[row + g.hd + d];
+    if (do_right) a[row + g.x - g.hd + d] = a[row + g.x - g.hd - 1 - d];
+}
+// local_halos.cpp:57-102 (update_top / update_bottom): every column kk in [0,x).
+__global__ void k_halo_tb(Geo g, FieldList fl, int depth, int do_top, int do_bottom)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kk >= g.x) return;
+    double* a = fl.f[blockIdx.y];
+    for (int d = 0; d < depth; ++d) {
+        if (do_top) a[(long)g.off + (long)(g.y - g.hd + d) * g.pitch + kk] =
+            a[(long)g.off + (long)(g.y - g.hd - 1 - d) * g.pitch + kk];
+        if (do_bottom) a[(long)g.off + (long)(g.hd - 1 - d) * g.pitch + kk] =
+            a[(long)g.off + (long)(g.hd + d) * g.pitch + kk];
+    }
+}
+
+// kernel_interface.cpp:100-127: per flagged field, faces L, R, T, B where the neighbour is external.
+// L/R of all fields in one launch, then T/B in a second (T/B reads the columns L/R just wrote).
+int tlk_local_halos(tl_chunk* c, const int fields[6], int depth)
+{
+    FieldList fl;
+    fl.n = 0;
+    for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i)
+        if (fields[i]) fl.f[fl.n++] = c->f[i];
+    if (!fl.n) return TL_OK;
+    const int L = c->nb[TL_FACE_LEFT] == TL_EXTERNAL_FACE, R = c->nb[TL_FACE_RIGHT] == TL_EXTERNAL_FACE;
+    const int T = c->nb[TL_FACE_TOP] == TL_EXTERNAL_FACE, B = c->nb[TL_FACE_BOTTOM] == TL_EXTERNAL_FACE;
+    if (L || R) {
+        dim3 grid((c->g.y * depth + 127) / 128, fl.n);
+        k_halo_lr<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, L, R);
+        ++g_tl_launches;
+    }
+    if (T || B) {
+        dim3 grid((c->g.x + 127) / 128, fl.n);
+        k_halo_tb<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, T, B);
+        ++g_tl_launches;
+    }
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// pack_halos.cpp:7-184.  Buffer index b: L/R  b = jj*depth + d ; T/B  b = d*x + kk.  Fields are
+// concatenated in exchange-index order, depth*y (L/R) or depth*x (T/B) doubles each
+// (remote_halo_driver.c:132-184).
+__global__ void k_pack(Geo g, FieldList fl, int depth, int face, int pack, double* buf)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+    const int per_field = depth * (lr ? g.y : g.x);
+    if (b >= per_field) return;
+    double* a = fl.f[blockIdx.y];
+    double* bp = buf + (size_t)blockIdx.y * per_field + b;
+    int jj, kk;
+    if (lr) {
+        jj = b / depth;
+        const int d = b % depth;
+        if (face == TL_FACE_LEFT) kk = pack ? g.hd + d : g.hd - depth + d;
+        else kk = pack ? g.x - g.hd - depth + d : g.x - g.hd + d;
+    } else {
+        const int d = b / g.x;
+        kk = b % g.x;
+        if (face == TL_FACE_TOP) jj = pack ? g.y - g.hd - depth + d : g.y - g.hd + d;
+        else jj = pack ? g.hd + d : g.hd - depth + d;
+    }
+    const long i = (long)g.off + (long)jj * g.pitch + kk;
+    if (pack) *bp = a[i];
+    else a[i] = *bp;
+}
+
+int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len)
+{
+    FieldList fl;
+    fl.n = 0;
+    for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i)
+        if (fields[i]) fl.f[fl.n++] = c->f[i];
+    const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+    const int per_field = depth * (lr ? c->g.y : c->g.x);
+    if (len) *len = per_field * fl.n;
+    if (!fl.n) return TL_OK;
+    dim3 grid((per_field + 127) / 128, fl.n);
+    k_pack<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, face, pack ? 1 : 0, devbuf);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// CG
+// ---------------------------------------------------------------------------------------------
+// cg.cpp:7-134 via kernel_interface.cpp:192-210: cg_init_u, cg_init_k, cg_init_others (+ r.p)
+int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry)
+{
+    double *p = c->f[TL_FIELD_P], *r = c->f[TL_FIELD_R], *u = c->f[TL_FIELD_U], *w = c->f[TL_FIELD_W];
+    double *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const double *den = c->f[TL_FIELD_DENSITY], *en = c->f[TL_FIELD_ENERGY1];
+    const int x = c->g.x, y = c->g.y, hd = c->g.hd, pitch = c->g.pitch;
+    TL_TRY(launch_generic<0>(c, ALL_RANGE(c),
+                             [=] __device__(long i, int jj, int kk, double*) {
+                                 p[i] = 0.0;
+                                 r[i] = 0.0;
+                                 u[i] = en[i] * den[i];
+                                 if (jj > 0 && jj < y - 1 && kk > 0 && kk < x - 1)
+                                     w[i] = (coefficient == TL_CONDUCTIVITY) ? den[i] : 1.0 / den[i];
+                             },
+                             NoFin()));
+    TL_TRY(launch_generic<0>(c, hd, x - 1, hd, y - 1,
+                             [=] __device__(long i, int, int, double*) {
+                                 kx[i] = rx * (w[i - 1] + w[i]) / (2.0 * w[i - 1] * w[i]);
+                                 ky[i] = ry * (w[i - pitch] + w[i]) / (2.0 * w[i - pitch] * w[i]);
+                             },
+                             NoFin()));
+    return launch_generic<1>(
+        c, INTERIOR_RANGE(c),
+        [=] __device__(long i, int, int, double* acc) {
+            const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], u[i], u[i - 1], u[i + 1],
+                                  u[i - pitch], u[i + pitch]);
+            w[i] = s;
+            const double rv = u[i] - s;
+            r[i] = rv;
+            p[i] = rv;
+            acc[0] += rv * rv;
+        },
+        [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
+}
+
+__global__ void k_seed_rro(DevScal* S) { S->rro = S->sums[0]; }
+int tlk_seed_rro(tl_chunk* c)
+{
+    k_seed_rro<<<1, 1, 0, c->stream>>>(c->scal);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+__global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
+{
+    S->rro = S->pw = S->rrn = S->alpha = S->beta = 0.0;
+    S->error = 1e+10; // diffuse.c:44
+    S->eps = eps;
+    S->iters = 0;
+    S->conv = 0;
+    S->p_pending = 0;
+    S->max_iters = max_iters;
+    S->conv_mode = 0;
+    S->pad = 0u;
+    S->counter[0] = 0u;
+}
+int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
+{
+    c->resident_iters = 0;
+    k_reset_scal<<<1, 1, 0, c->stream>>>(c->scal, eps, max_iters);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// Hot-kernel tile: TL_TPB threads x 2 columns, ROWS rows.  kk is the first of the thread's two
+// columns; (off + kk) is even by construction, so double2 accesses are 16-byte aligned and a warp
+// covers 512 contiguous, 128-byte-aligned bytes of a row.
+struct HotTile {
+    int kk, j0, j1, tile, ntiles;
+    bool v0, v1;
+    long i;
+};
+template <int ROWS>
+__device__ __forceinline__ HotTile hot_tile(const Geo& g, int rev)
+{
+    HotTile t;
+    const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+    const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    t.kk = g.hd + 2 * (bx * TL_TPB + threadIdx.x);
+    t.v0 = t.kk < g.x - g.hd;
+    t.v1 = t.kk + 1 < g.x - g.hd;
+    t.j0 = g.hd + by * ROWS;
+    t.j1 = min(t.j0 + ROWS, g.y - g.hd);
+    t.i = (long)g.off + (long)t.j0 * g.pitch + t.kk;
+    t.tile = by * gridDim.x + bx;
+    t.ntiles = gridDim.x * gridDim.y;
+    return t;
+}
+
+#define HOT_ROWS 16
+
+// cg.cpp:137-195 cg_calc_w:  w = A p (5-point SMVP) fused with the p.w dot product.
+// 32 B/cell of HBM traffic: read p, kx, ky; write w.  Rows j-1, j, j+1 of p and rows j, j+1 of ky
+// slide through registers, so every element is requested from L2 once per tile.
+template <int ROWS>
+__global__ void __launch_bounds__(TL_TPB)
+k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, const double* __restrict__ ky,
+            double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rev)
+{
+    DevScal* S = ra.S;
+    if (mode == SCAL_DEV) {
+        const int conv = S->conv;
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S->p_pending = 0;
+        if (conv) return;
+    }
+    const HotTile t = hot_tile<ROWS>(g, rev);
+    double acc[1] = {0.0};
+    if (t.v0) {
+        long i = t.i;
+        const int pitch = g.pitch;
+        double2 pm = ld2_ro(p + i - pitch);
+        double2 pc = ld2_ro(p + i);
+        double pl = __ldg(p + i - 1), pr = __ldg(p + i + 2);
+        double2 kyc = ld2_ro(ky + i);
+#pragma unroll 4
+        for (int jj = t.j0; jj < t.j1; ++jj, i += pitch) {
+            const double2 pn = ld2_ro(p + i + pitch);
+            const double2 kyn = ld2_ro(ky + i + pitch);
+            const double2 kxc = ld2_ro(kx + i);
+            const double kxr = __ldg(kx + i + 2);
+            const double pln = __ldg(p + i + pitch - 1), prn = __ldg(p + i + pitch + 2);
+            double2 wv;
+            wv.x = smvp(kxc.x, kxc.y, kyc.x, kyn.x, pc.x, pl, pc.y, pm.x, pn.x);
+            wv.y = smvp(kxc.y, kxr, kyc.y, kyn.y, pc.y, pc.x, pr, pm.y, pn.y);
+            st_pair(w + i, wv, t.v1);
+            acc[0] += wv.x * pc.x;
+            if (t.v1) acc[0] += wv.y * pc.y;
+            pm = pc; pc = pn; kyc = kyn; pl = pln; pr = prn;
+        }
+    }
+    double tot[1];
+    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        S->pw = tot[0];
+        if (mode == SCAL_DEV) {
+            const double alpha = S->rro / tot[0]; // cg_driver.c:87
+            S->alpha = alpha;
+            d_alphas[S->iters] = alpha;           // cg_driver.c:93
+        }
+    }
+}
+
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev)
+{
+    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
+    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    k_cg_calc_w<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],
+                                                         c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas,
+                                                         ra, (int)mode, rev ? 1 : 0);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// cg.cpp:198-254 cg_calc_ur:  u += alpha p ; r -= alpha w ; fused with the r.r reduction.
+// 48 B/cell: read u, p, r, w; write u, r.
+template <int ROWS>
+__global__ void __launch_bounds__(TL_TPB)
+k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double* __restrict__ p,
+             const double* __restrict__ w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
+             int rev)
+{
+    DevScal* S = ra.S;
+    double alpha = alpha_imm;
+    if (mode == SCAL_DEV) {
+        if (S->conv) return;
+        alpha = S->alpha;
+    }
+    const HotTile t = hot_tile<ROWS>(g, rev);
+    double acc[1] = {0.0};
+    if (t.v0) {
+        long i = t.i;
+#pragma unroll 4
+        for (int jj = t.j0; jj < t.j1; ++jj, i += g.pitch) {
+            double2 uv = ld2(u + i), rv = ld2(r + i);
+            const double2 pv = ld2_ro(p + i), wv = ld2_ro(w + i);
+            uv.x = uv.x + alpha * pv.x;
+            uv.y = uv.y + alpha * pv.y;
+            rv.x = rv.x - alpha * wv.x;
+            rv.y = rv.y - alpha * wv.y;
+            st_pair(u + i, uv, t.v1);
+            st_pair(r + i, rv, t.v1);
+            acc[0] += rv.x * rv.x;
+            if (t.v1) acc[0] += rv.y * rv.y;
+        }
+    }
+    double tot[1];
+    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        S->rrn = tot[0];
+        if (mode == SCAL_DEV) {
+            const double rrn = tot[0];
+            const double beta = rrn / S->rro; // cg_driver.c:106
+            S->beta = beta;
+            d_betas[S->iters] = beta;         // cg_driver.c:111
+            S->error = rrn;                   // cg_driver.c:122-123
+            S->rro = rrn;
+            S->iters = S->iters + 1;
+            S->p_pending = 1;
+            const bool hit = S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
+            if (hit || S->iters >= S->max_iters) S->conv = 1; // cg_driver.c:18,24; cheby_driver.c:70
+        }
+    }
+}
+
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev)
+{
+    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
+    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    k_cg_calc_ur<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],
+                                                          c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra,
+                                                          (int)mode, alpha, rev ? 1 : 0);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// cg.cpp:257-281 cg_calc_p:  p = beta p + r.  24 B/cell.
+// fuse_halo: the CTAs that own chunk-edge cells also write the depth-1 reflective halo of p on
+// external faces (local_halos.cpp, depth 1) so the resident loop needs no separate halo launches.
+template <int ROWS>
+__global__ void __launch_bounds__(TL_TPB)
+k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal* S, int mode, double beta_imm,
+            int rev, int halo_mask)
+{
+    double beta = beta_imm;
+    if (mode == SCAL_DEV) {
+        if (!S->p_pending) return;
+        beta = S->beta;
+    }
+    const HotTile t = hot_tile<ROWS>(g, rev);
+    if (!t.v0) return;
+    long i = t.i;
+    const bool left_edge = (halo_mask & 1) && t.kk == g.hd;
+    const int last = g.x - g.hd - 1;
+    const bool right0 = (halo_mask & 2) && t.kk == last, right1 = (halo_mask & 2) && t.kk + 1 == last;
+#pragma unroll 4
+    for (int jj = t.j0; jj < t.j1; ++jj, i += g.pitch) {
+        double2 pv = ld2(p + i);
+        const double2 rv = ld2_ro(r + i);
+        pv.x = beta * pv.x + rv.x;
+        pv.y = beta * pv.y + rv.y;
+        st_pair(p + i, pv, t.v1);
+        if (halo_mask) {
+            const bool bot = (halo_mask & 4) && jj == g.hd, top = (halo_mask & 8) && jj == g.y - g.hd - 1;
+            if (left_edge) p[i - 1] = pv.x;
+            if (right0) p[i + 1] = pv.x;
+            if (right1) p[i + 2] = pv.y;
+            if (bot) {
+                st_pair(p + i - g.pitch, pv, t.v1);
+                if (left_edge) p[i - g.pitch - 1] = pv.x;
+                if (right0) p[i - g.pitch + 1] = pv.x;
+                if (right1) p[i - g.pitch + 2] = pv.y;
+            }
+            if (top) {
+                st_pair(p + i + g.pitch, pv, t.v1);
+                if (left_edge) p[i + g.pitch - 1] = pv.x;
+                if (right0) p[i + g.pitch + 1] = pv.x;
+                if (right1) p[i + g.pitch + 2] = pv.y;
+            }
+        }
+    }
+}
+
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo)
+{
+    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
+    int mask = 0;
+    if (fuse_halo) {
+        if (c->nb[TL_FACE_LEFT] == TL_EXTERNAL_FACE) mask |= 1;
+        if (c->nb[TL_FACE_RIGHT] == TL_EXTERNAL_FACE) mask |= 2;
+        if (c->nb[TL_FACE_BOTTOM] == TL_EXTERNAL_FACE) mask |= 4;
+        if (c->nb[TL_FACE_TOP] == TL_EXTERNAL_FACE) mask |= 8;
+    }
+    k_cg_calc_p<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal,
+                                                         (int)mode, beta, rev ? 1 : 0, mask);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
+// Fused  p = beta p + r  (cg.cpp:257-281, of iteration t-1)  +  w = A p ; p.w  (cg.cpp:137-195, of
+// iteration t).  48 B/cell instead of 24 + 32: read p, r, kx, ky; write p, w.  The updated p of the
+// one-cell ring around the tile is recomputed from (p, r) of the neighbouring cells -- bit-identical
+// to what the owning tile stores -- with the reflective boundary applied on external faces by index
+// mirroring, so no halo of p or r is read and none has to be exchanged on a single chunk.
+// Old p is read by neighbouring tiles while this tile overwrites it, so the update is double
+// buffered: reads come from `p_in`, writes go to `p_out` (the chunk's P and SD buffers swap roles).
+template <int ROWS>
+__global__ void __launch_bounds__(TL_TPB)
+k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out, const double* __restrict__ r,
+             const double* __restrict__ kx, const double* __restrict__ ky, double* __restrict__ w,
+             double* __restrict__ d_alphas, RedArgs ra, int first, int rev)
+{
+    DevScal* S = ra.S;
+    if (S->conv) return;
+    const double beta = first ? 0.0 : S->beta;
+    const HotTile t = hot_tile<ROWS>(g, rev);
+    double acc[1] = {0.0};
+    if (t.v0) {
+        const int pitch = g.pitch;
+        const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
+        // mirrored column offsets for the left / right neighbours of my two cells
+        const int dl = (t.kk - 1 < klo) ? 0 : -1;                 // left neighbour of cell 0
+        const int dr = (t.kk + 2 > khi) ? ((t.kk + 1 > khi) ? 0 : 1) : 2; // right neighbour of cell 1
+        auto pnew2 = [&](long i) {
+            double2 a = ld2_ro(p_in + i);
+            const double2 b = ld2_ro(r + i);
+            if (!first) { a.x = beta * a.x + b.x; a.y = beta * a.y + b.y; }
+            return a;
+        };
+        auto pnew1 = [&](long i) {
+            double a = __ldg(p_in + i);
+            if (!first) a = beta * a + __ldg(r + i);
+            return a;
+        };
+        long i = t.i;
+        const long im = (t.j0 - 1 < jlo) ? i : i - pitch; // reflective: row below the first = itself
+        double2 pm = pnew2(im);
+        double2 pc = pnew2(i);
+        double pl = pnew1(i + dl), pr = pnew1(i + dr);
+        double2 kyc = ld2_ro(ky + i);
+        for (int jj = t.j0; jj < t.j1; ++jj, i += pitch) {
+            const long in = (jj + 1 > jhi) ? i : i + pitch;
+            const double2 pn = pnew2(in);
+            const double pln = pnew1(in + dl), prn = pnew1(in + dr);
+            const double2 kyn = ld2_ro(ky + i + pitch);
+            const double2 kxc = ld2_ro(kx + i);
+            const double kxr = __ldg(kx + i + 2);
+            double2 wv;
+            wv.x = smvp(kxc.x, kxc.y, kyc.x, kyn.x, pc.x, pl, t.v1 ? pc.y : pc.x, pm.x, pn.x);
+            wv.y = smvp(kxc.y, kxr, kyc.y, kyn.y, pc.y, pc.x, pr, pm.y, pn.y);
+            st_pair(w + i, wv, t.v1);
+            st_pair(p_out + i, pc, t.v1);
+            acc[0] += wv.x * pc.x;
+            if (t.v1) acc[0] += wv.y * pc.y;
+            pm = pc; pc = pn; kyc = kyn; pl = pln; pr = prn;
+        }
+    }
+    double tot[1];
+    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        S->pw = tot[0];
+        const double alpha = S->rro / tot[0];
+        S->alpha = alpha;
+        d_alphas[S->iters] = alpha;
+        S->p_pending = 0;
+    }
+}
+
+int tlk_cg_calc_pw(tl_chunk* c, bool first, bool rev)
+{
+    (void)c; (void)first; (void)rev;
+    tl_set_error("fused p+w kernel is not enabled in this build");
+    return TL_ERR_ARG;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Chebyshev (cheby.cpp), PPCG (ppcg.cpp), Jacobi (jacobi.cpp), shared solver kernels
+// ---------------------------------------------------------------------------------------------
+// cheby.cpp:7-43
+int tlk_cheby_init(tl_chunk* c, double theta)
+{
+    double *p = c->f[TL_FIELD_P], *r = c->f[TL_FIELD_R], *w = c->f[TL_FIELD_W];
+    const double *u = c->f[TL_FIELD_U], *u0 = c->f[TL_FIELD_U0], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const int pitch = c->g.pitch;
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) {
+                                 const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], u[i], u[i - 1],
+                                                       u[i + 1], u[i - pitch], u[i + pitch]);
+                                 w[i] = s;
+                                 const double rv = u0[i] - s;
+                                 r[i] = rv;
+                                 p[i] = rv / theta;
+                             },
+                             NoFin());
+}
+// cheby.cpp:73-110
+int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta)
+{
+    double *p = c->f[TL_FIELD_P], *r = c->f[TL_FIELD_R], *w = c->f[TL_FIELD_W];
+    const double *u = c->f[TL_FIELD_U], *u0 = c->f[TL_FIELD_U0], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const int pitch = c->g.pitch;
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) {
+                                 const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], u[i], u[i - 1],
+                                                       u[i + 1], u[i - pitch], u[i + pitch]);
+                                 w[i] = s;
+                                 const double rv = u0[i] - s;
+                                 r[i] = rv;
+                                 p[i] = alpha * p[i] + beta * rv;
+                             },
+                             NoFin());
+}
+// cheby.cpp:46-70
+int tlk_cheby_calc_u(tl_chunk* c)
+{
+    double* u = c->f[TL_FIELD_U];
+    const double* p = c->f[TL_FIELD_P];
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) { u[i] += p[i]; }, NoFin());
+}
+// ppcg.cpp:7-31
+int tlk_ppcg_init(tl_chunk* c, double theta)
+{
+    double* sd = c->f[TL_FIELD_SD];
+    const double* r = c->f[TL_FIELD_R];
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) { sd[i] = r[i] / theta; }, NoFin());
+}
+// ppcg.cpp:34-66
+int tlk_ppcg_calc_ur(tl_chunk* c)
+{
+    double *r = c->f[TL_FIELD_R], *u = c->f[TL_FIELD_U];
+    const double *sd = c->f[TL_FIELD_SD], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const int pitch = c->g.pitch;
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) {
+                                 const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], sd[i], sd[i - 1],
+                                                       sd[i + 1], sd[i - pitch], sd[i + pitch]);
+                                 r[i] -= s;
+                                 u[i] += sd[i];
+                             },
+                             NoFin());
+}
+// ppcg.cpp:69-94
+int tlk_ppcg_calc_sd(tl_chunk* c, double alpha, double beta)
+{
+    double* sd = c->f[TL_FIELD_SD];
+    const double* r = c->f[TL_FIELD_R];
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) { sd[i] = alpha * sd[i] + beta * r[i]; },
+                             NoFin());
+}
+// jacobi.cpp:7-54
+int tlk_jacobi_init(tl_chunk* c, int coefficient, double rx, double ry)
+{
+    double *u = c->f[TL_FIELD_U], *u0 = c->f[TL_FIELD_U0], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const double *den = c->f[TL_FIELD_DENSITY], *en = c->f[TL_FIELD_ENERGY1];
+    const int x = c->g.x, y = c->g.y, hd = c->g.hd, pitch = c->g.pitch;
+    return launch_generic<0>(
+        c, ALL_RANGE(c),
+        [=] __device__(long i, int jj, int kk, double*) {
+            if (kk > 0 && kk < x - 1 && jj > 0 && jj < y - 1) {
+                const double v = en[i] * den[i];
+                u0[i] = v;
+                u[i] = v;
+            }
+            if (jj >= hd && jj < y - 1 && kk >= hd && kk < x - 1) {
+                const bool cnd = (coefficient == TL_CONDUCTIVITY);
+                const double dc = cnd ? den[i] : 1.0 / den[i];
+                const double dl = cnd ? den[i - 1] : 1.0 / den[i - 1];
+                const double dd = cnd ? den[i - pitch] : 1.0 / den[i - pitch];
+                kx[i] = rx * (dl + dc) / (2.0 * dl * dc);
+                ky[i] = ry * (dd + dc) / (2.0 * dd * dc);
+            }
+        },
+        NoFin());
+}
+// kernel_interface.cpp:287-300: jacobi_copy_u (all cells) then jacobi_iterate (jacobi.cpp:57-117)
+int tlk_jacobi_iterate(tl_chunk* c)
+{
+    TL_TRY(tlk_copy_field(c, TL_FIELD_R, TL_FIELD_U, false));
+    double* u = c->f[TL_FIELD_U];
+    const double *u0 = c->f[TL_FIELD_U0], *r = c->f[TL_FIELD_R], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const int pitch = c->g.pitch;
+    return launch_generic<1>(
+        c, INTERIOR_RANGE(c),
+        [=] __device__(long i, int, int, double* acc) {
+            const double v = (u0[i] + (kx[i + 1] * r[i + 1] + kx[i] * r[i - 1]) +
+                              (ky[i + pitch] * r[i + pitch] + ky[i] * r[i - pitch])) /
+                             (1.0 + (kx[i] + kx[i + 1]) + (ky[i] + ky[i + pitch]));
+            u[i] = v;
+            acc[0] += fabs(v - r[i]);
+        },
+        [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
+}
+// solver_methods.cpp:34-65
+int tlk_calculate_residual(tl_chunk* c)
+{
+    double* r = c->f[TL_FIELD_R];
+    const double *u = c->f[TL_FIELD_U], *u0 = c->f[TL_FIELD_U0], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
+    const int pitch = c->g.pitch;
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) {
+                                 const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], u[i], u[i - 1],
+                                                       u[i + 1], u[i - pitch], u[i + pitch]);
+                                 r[i] = u0[i] - s;
+                             },
+                             NoFin());
+}
+// solver_methods.cpp:68-117
+int tlk_calculate_2norm(tl_chunk* c, int field)
+{
+    const double* b = c->f[field];
+    return launch_generic<1>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double* acc) { acc[0] += b[i] * b[i]; },
+                             [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
+}
+// solver_methods.cpp:120-145
+int tlk_finalise(tl_chunk* c)
+{
+    double* en = c->f[TL_FIELD_ENERGY1];
+    const double *u = c->f[TL_FIELD_U], *den = c->f[TL_FIELD_DENSITY];
+    return launch_generic<0>(c, INTERIOR_RANGE(c),
+                             [=] __device__(long i, int, int, double*) { en[i] = u[i] / den[i]; }, NoFin());
+}
