@@ -112,6 +112,7 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int f = 0; f < TL_NUM_FIELDS; ++f) cudaFree(c->f[f]);
+    if (c->p2) cudaFree(c->p2);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->scal); cudaFreeHost(c->scal_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas); cudaFree(c->d_cheby);

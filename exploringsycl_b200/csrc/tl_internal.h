@@ -60,6 +60,7 @@ struct tl_chunk {
     size_t field_elems;           // allocated doubles per 2-D field
     double* f[TL_NUM_FIELDS];     // device
     double *cell_x, *cell_y, *vertex_x, *vertex_y; // device 1-D
+    double* p2;                   // device, second p buffer of the fused p+w kernel (lazily allocated)
     double* partials;             // device, per-tile partial sums (4 lanes)
     int partial_cap;              // tiles
     DevScal* scal;                // device
@@ -124,7 +125,7 @@ int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev);                // -> scal->pw (& alpha when SCAL_DEV)
 int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev); // -> scal->rrn (& beta, conv when SCAL_DEV)
 int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo);
-int tlk_cg_calc_pw(tl_chunk* c, bool first, bool rev);                 // fused p-update + matvec (SCAL_DEV only)
+int tlk_cg_calc_pw(tl_chunk* c, bool rev);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
 int tlk_cheby_calc_u(tl_chunk* c);

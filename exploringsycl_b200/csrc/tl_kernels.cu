@@ -432,7 +432,7 @@ int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
     return TL_OK;
 }
 
-// Hot-kernel tile: TL_TPB threads x 2 columns, ROWS rows.  kk is the first of the thread's two
+// Hot-kernel tile: TL_TPB threads x 2 columns, `rows` rows.  kk is the first of the thread's two
 // columns; (off + kk) is even by construction, so double2 accesses are 16-byte aligned and a warp
 // covers 512 contiguous, 128-byte-aligned bytes of a row.
 struct HotTile {
@@ -440,8 +440,7 @@ struct HotTile {
     bool v0, v1;
     long i;
 };
-template <int ROWS>
-__device__ __forceinline__ HotTile hot_tile(const Geo& g, int rev)
+__device__ __forceinline__ HotTile hot_tile(const Geo& g, int rows, int rev)
 {
     HotTile t;
     const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
@@ -449,23 +448,63 @@ __device__ __forceinline__ HotTile hot_tile(const Geo& g, int rev)
     t.kk = g.hd + 2 * (bx * TL_TPB + threadIdx.x);
     t.v0 = t.kk < g.x - g.hd;
     t.v1 = t.kk + 1 < g.x - g.hd;
-    t.j0 = g.hd + by * ROWS;
-    t.j1 = min(t.j0 + ROWS, g.y - g.hd);
+    t.j0 = g.hd + by * rows;
+    t.j1 = min(t.j0 + rows, g.y - g.hd);
     t.i = (long)g.off + (long)t.j0 * g.pitch + t.kk;
     t.tile = by * gridDim.x + bx;
     t.ntiles = gridDim.x * gridDim.y;
     return t;
 }
 
-#define HOT_ROWS 16
+// Tuning knobs (tl_set_tuning): rows per tile and rows per load batch for each hot kernel family.
+// The load batch U is the number of rows whose loads are issued back to back before any of them is
+// consumed: it sets the bytes each thread keeps in flight (the kernels are latency-bound, not
+// issue-bound; see DESIGN.md "in-flight bytes").
+enum { TUNE_W = 0, TUNE_UR = 1, TUNE_P = 2, TUNE_PW = 3 };
+// rows == 0 selects the built-in heuristic (tile_rows).  Defaults from the round-1 sweep on B200
+// (profiles/tuning_r01.txt): stencil kernels want tall tiles (the two extra rows of p per tile are
+// re-read from L2), the streaming kernels want many small tiles (better tail balance).
+static int g_rows[4] = {0, 0, 0, 0};
+static int g_batch[4] = {2, 4, 4, 1};
+extern "C" int tl_set_tuning(int kernel, int rows, int batch)
+{
+    if (kernel < 0 || kernel > 3 || rows < 0 || rows > 256 || (batch != 1 && batch != 2 && batch != 4)) {
+        tl_set_error("tl_set_tuning: bad arguments");
+        return TL_ERR_ARG;
+    }
+    g_rows[kernel] = rows;
+    g_batch[kernel] = batch;
+    return TL_OK;
+}
+static int tile_rows(const tl_chunk* c, int kernel)
+{
+    if (g_rows[kernel] > 0) return g_rows[kernel];
+    if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
+    const int colb = (c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS;
+    for (int rows = 64; rows > 8; rows >>= 1)
+        if ((long)colb * ((c->ny + rows - 1) / rows) >= 6 * 148) return rows; // >= 6 CTAs per SM
+    return 8;
+}
+static dim3 hot_grid(const tl_chunk* c, int rows)
+{
+    return dim3((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + rows - 1) / rows);
+}
+static int hot_check(const tl_chunk* c, dim3 grid)
+{
+    if ((long)grid.x * grid.y > c->partial_cap) {
+        tl_set_error("partials capacity exceeded");
+        return TL_ERR_ARG;
+    }
+    return TL_OK;
+}
 
 // cg.cpp:137-195 cg_calc_w:  w = A p (5-point SMVP) fused with the p.w dot product.
 // 32 B/cell of HBM traffic: read p, kx, ky; write w.  Rows j-1, j, j+1 of p and rows j, j+1 of ky
 // slide through registers, so every element is requested from L2 once per tile.
-template <int ROWS>
+template <int U>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, const double* __restrict__ ky,
-            double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rev)
+            double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev)
 {
     DevScal* S = ra.S;
     if (mode == SCAL_DEV) {
@@ -473,29 +512,42 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
         if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S->p_pending = 0;
         if (conv) return;
     }
-    const HotTile t = hot_tile<ROWS>(g, rev);
+    const HotTile t = hot_tile(g, rows, rev);
     double acc[1] = {0.0};
     if (t.v0) {
         long i = t.i;
-        const int pitch = g.pitch;
+        const long pitch = g.pitch;
         double2 pm = ld2_ro(p + i - pitch);
         double2 pc = ld2_ro(p + i);
         double pl = __ldg(p + i - 1), pr = __ldg(p + i + 2);
         double2 kyc = ld2_ro(ky + i);
-#pragma unroll 4
-        for (int jj = t.j0; jj < t.j1; ++jj, i += pitch) {
-            const double2 pn = ld2_ro(p + i + pitch);
-            const double2 kyn = ld2_ro(ky + i + pitch);
-            const double2 kxc = ld2_ro(kx + i);
-            const double kxr = __ldg(kx + i + 2);
-            const double pln = __ldg(p + i + pitch - 1), prn = __ldg(p + i + pitch + 2);
-            double2 wv;
-            wv.x = smvp(kxc.x, kxc.y, kyc.x, kyn.x, pc.x, pl, pc.y, pm.x, pn.x);
-            wv.y = smvp(kxc.y, kxr, kyc.y, kyn.y, pc.y, pc.x, pr, pm.y, pn.y);
-            st_pair(w + i, wv, t.v1);
-            acc[0] += wv.x * pc.x;
-            if (t.v1) acc[0] += wv.y * pc.y;
-            pm = pc; pc = pn; kyc = kyn; pl = pln; pr = prn;
+        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+            double2 pn[U], kyn[U], kxc[U];
+            double kxr[U], pln[U], prn[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (jb + u < t.j1) {
+                    const long iu = i + u * pitch;
+                    pn[u] = ld2_ro(p + iu + pitch);
+                    kyn[u] = ld2_ro(ky + iu + pitch);
+                    kxc[u] = ld2_ro(kx + iu);
+                    kxr[u] = __ldg(kx + iu + 2);
+                    pln[u] = __ldg(p + iu + pitch - 1);
+                    prn[u] = __ldg(p + iu + pitch + 2);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (jb + u < t.j1) {
+                    double2 wv;
+                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pc.y, pm.x, pn[u].x);
+                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
+                    st_pair(w + i + u * pitch, wv, t.v1);
+                    acc[0] += wv.x * pc.x;
+                    if (t.v1) acc[0] += wv.y * pc.y;
+                    pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln[u]; pr = prn[u];
+                }
+            }
         }
     }
     double tot[1];
@@ -511,11 +563,19 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
 
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev)
 {
-    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
+    const int rows = tile_rows(c, TUNE_W);
+    dim3 grid = hot_grid(c, rows);
+    TL_TRY(hot_check(c, grid));
     RedArgs ra{c->partials, c->partial_cap, c->scal};
-    k_cg_calc_w<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],
-                                                         c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas,
-                                                         ra, (int)mode, rev ? 1 : 0);
+#define LAUNCH_W(U)                                                                                          \
+    k_cg_calc_w<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], \
+                                                  c->f[TL_FIELD_W], c->d_alphas, ra, (int)mode, rows, rev ? 1 : 0)
+    switch (g_batch[TUNE_W]) {
+    case 1: LAUNCH_W(1); break;
+    case 2: LAUNCH_W(2); break;
+    default: LAUNCH_W(4); break;
+    }
+#undef LAUNCH_W
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     return TL_OK;
@@ -523,11 +583,11 @@ int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev)
 
 // cg.cpp:198-254 cg_calc_ur:  u += alpha p ; r -= alpha w ; fused with the r.r reduction.
 // 48 B/cell: read u, p, r, w; write u, r.
-template <int ROWS>
+template <int U>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double* __restrict__ p,
              const double* __restrict__ w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
-             int rev)
+             int rows, int rev)
 {
     DevScal* S = ra.S;
     double alpha = alpha_imm;
@@ -535,22 +595,37 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
         if (S->conv) return;
         alpha = S->alpha;
     }
-    const HotTile t = hot_tile<ROWS>(g, rev);
+    const HotTile t = hot_tile(g, rows, rev);
     double acc[1] = {0.0};
     if (t.v0) {
         long i = t.i;
-#pragma unroll 4
-        for (int jj = t.j0; jj < t.j1; ++jj, i += g.pitch) {
-            double2 uv = ld2(u + i), rv = ld2(r + i);
-            const double2 pv = ld2_ro(p + i), wv = ld2_ro(w + i);
-            uv.x = uv.x + alpha * pv.x;
-            uv.y = uv.y + alpha * pv.y;
-            rv.x = rv.x - alpha * wv.x;
-            rv.y = rv.y - alpha * wv.y;
-            st_pair(u + i, uv, t.v1);
-            st_pair(r + i, rv, t.v1);
-            acc[0] += rv.x * rv.x;
-            if (t.v1) acc[0] += rv.y * rv.y;
+        const long pitch = g.pitch;
+        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+            double2 uv[U], rv[U], pv[U], wv[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (jb + q < t.j1) {
+                    const long iq = i + q * pitch;
+                    uv[q] = ld2(u + iq);
+                    rv[q] = ld2(r + iq);
+                    pv[q] = ld2_ro(p + iq);
+                    wv[q] = ld2_ro(w + iq);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (jb + q < t.j1) {
+                    const long iq = i + q * pitch;
+                    uv[q].x = uv[q].x + alpha * pv[q].x;
+                    uv[q].y = uv[q].y + alpha * pv[q].y;
+                    rv[q].x = rv[q].x - alpha * wv[q].x;
+                    rv[q].y = rv[q].y - alpha * wv[q].y;
+                    st_pair(u + iq, uv[q], t.v1);
+                    st_pair(r + iq, rv[q], t.v1);
+                    acc[0] += rv[q].x * rv[q].x;
+                    if (t.v1) acc[0] += rv[q].y * rv[q].y;
+                }
+            }
         }
     }
     double tot[1];
@@ -573,136 +648,216 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
 
 int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev)
 {
-    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
+    const int rows = tile_rows(c, TUNE_UR);
+    dim3 grid = hot_grid(c, rows);
+    TL_TRY(hot_check(c, grid));
     RedArgs ra{c->partials, c->partial_cap, c->scal};
-    k_cg_calc_ur<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],
-                                                          c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra,
-                                                          (int)mode, alpha, rev ? 1 : 0);
+#define LAUNCH_UR(U)                                                                                       \
+    k_cg_calc_ur<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R], c->f[TL_FIELD_P], \
+                                                   c->f[TL_FIELD_W], c->d_betas, ra, (int)mode, alpha, rows,    \
+                                                   rev ? 1 : 0)
+    switch (g_batch[TUNE_UR]) {
+    case 1: LAUNCH_UR(1); break;
+    case 2: LAUNCH_UR(2); break;
+    default: LAUNCH_UR(4); break;
+    }
+#undef LAUNCH_UR
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
 
+// Depth-1 reflective halo of p written by the thread that owns the edge cell (local_halos.cpp, depth 1,
+// external faces only; corners end up = double reflection exactly as L/R-then-T/B produces them).
+__device__ __forceinline__ void p_halo_store(const Geo& g, double* p, long i, int jj, double2 pv, const HotTile& t,
+                                             int halo_mask)
+{
+    const int last = g.x - g.hd - 1;
+    const bool left_edge = (halo_mask & 1) && t.kk == g.hd;
+    const bool right0 = (halo_mask & 2) && t.kk == last, right1 = (halo_mask & 2) && t.kk + 1 == last;
+    const bool bot = (halo_mask & 4) && jj == g.hd, top = (halo_mask & 8) && jj == g.y - g.hd - 1;
+    if (left_edge) p[i - 1] = pv.x;
+    if (right0) p[i + 1] = pv.x;
+    if (right1) p[i + 2] = pv.y;
+    if (bot) {
+        st_pair(p + i - g.pitch, pv, t.v1);
+        if (left_edge) p[i - g.pitch - 1] = pv.x;
+        if (right0) p[i - g.pitch + 1] = pv.x;
+        if (right1) p[i - g.pitch + 2] = pv.y;
+    }
+    if (top) {
+        st_pair(p + i + g.pitch, pv, t.v1);
+        if (left_edge) p[i + g.pitch - 1] = pv.x;
+        if (right0) p[i + g.pitch + 1] = pv.x;
+        if (right1) p[i + g.pitch + 2] = pv.y;
+    }
+}
+
 // cg.cpp:257-281 cg_calc_p:  p = beta p + r.  24 B/cell.
-// fuse_halo: the CTAs that own chunk-edge cells also write the depth-1 reflective halo of p on
-// external faces (local_halos.cpp, depth 1) so the resident loop needs no separate halo launches.
-template <int ROWS>
+// halo_mask != 0: the CTAs that own chunk-edge cells also write the depth-1 reflective halo of p on
+// the external faces in the mask, so the resident loop needs no separate halo launches.
+template <int U>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal* S, int mode, double beta_imm,
-            int rev, int halo_mask)
+            int rows, int rev, int halo_mask)
 {
     double beta = beta_imm;
     if (mode == SCAL_DEV) {
         if (!S->p_pending) return;
         beta = S->beta;
     }
-    const HotTile t = hot_tile<ROWS>(g, rev);
+    const HotTile t = hot_tile(g, rows, rev);
     if (!t.v0) return;
     long i = t.i;
-    const bool left_edge = (halo_mask & 1) && t.kk == g.hd;
-    const int last = g.x - g.hd - 1;
-    const bool right0 = (halo_mask & 2) && t.kk == last, right1 = (halo_mask & 2) && t.kk + 1 == last;
-#pragma unroll 4
-    for (int jj = t.j0; jj < t.j1; ++jj, i += g.pitch) {
-        double2 pv = ld2(p + i);
-        const double2 rv = ld2_ro(r + i);
-        pv.x = beta * pv.x + rv.x;
-        pv.y = beta * pv.y + rv.y;
-        st_pair(p + i, pv, t.v1);
-        if (halo_mask) {
-            const bool bot = (halo_mask & 4) && jj == g.hd, top = (halo_mask & 8) && jj == g.y - g.hd - 1;
-            if (left_edge) p[i - 1] = pv.x;
-            if (right0) p[i + 1] = pv.x;
-            if (right1) p[i + 2] = pv.y;
-            if (bot) {
-                st_pair(p + i - g.pitch, pv, t.v1);
-                if (left_edge) p[i - g.pitch - 1] = pv.x;
-                if (right0) p[i - g.pitch + 1] = pv.x;
-                if (right1) p[i - g.pitch + 2] = pv.y;
+    const long pitch = g.pitch;
+    const bool edge_tile = halo_mask && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
+                                         blockIdx.x == gridDim.x - 1);
+    for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+        double2 pv[U], rv[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                pv[q] = ld2(p + i + q * pitch);
+                rv[q] = ld2_ro(r + i + q * pitch);
             }
-            if (top) {
-                st_pair(p + i + g.pitch, pv, t.v1);
-                if (left_edge) p[i + g.pitch - 1] = pv.x;
-                if (right0) p[i + g.pitch + 1] = pv.x;
-                if (right1) p[i + g.pitch + 2] = pv.y;
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                pv[q].x = beta * pv[q].x + rv[q].x;
+                pv[q].y = beta * pv[q].y + rv[q].y;
+                st_pair(p + i + q * pitch, pv[q], t.v1);
             }
+        }
+        if (edge_tile) {
+#pragma unroll
+            for (int q = 0; q < U; ++q)
+                if (jb + q < t.j1) p_halo_store(g, p, i + q * pitch, jb + q, pv[q], t, halo_mask);
         }
     }
 }
 
+static int external_mask(const tl_chunk* c)
+{
+    int mask = 0;
+    if (c->nb[TL_FACE_LEFT] == TL_EXTERNAL_FACE) mask |= 1;
+    if (c->nb[TL_FACE_RIGHT] == TL_EXTERNAL_FACE) mask |= 2;
+    if (c->nb[TL_FACE_BOTTOM] == TL_EXTERNAL_FACE) mask |= 4;
+    if (c->nb[TL_FACE_TOP] == TL_EXTERNAL_FACE) mask |= 8;
+    return mask;
+}
+
 int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo)
 {
-    dim3 grid((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + HOT_ROWS - 1) / HOT_ROWS);
-    int mask = 0;
-    if (fuse_halo) {
-        if (c->nb[TL_FACE_LEFT] == TL_EXTERNAL_FACE) mask |= 1;
-        if (c->nb[TL_FACE_RIGHT] == TL_EXTERNAL_FACE) mask |= 2;
-        if (c->nb[TL_FACE_BOTTOM] == TL_EXTERNAL_FACE) mask |= 4;
-        if (c->nb[TL_FACE_TOP] == TL_EXTERNAL_FACE) mask |= 8;
+    const int rows = tile_rows(c, TUNE_P);
+    dim3 grid = hot_grid(c, rows);
+    const int mask = fuse_halo ? external_mask(c) : 0;
+#define LAUNCH_P(U)                                                                                         \
+    k_cg_calc_p<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal, (int)mode, \
+                                                  beta, rows, rev ? 1 : 0, mask)
+    switch (g_batch[TUNE_P]) {
+    case 1: LAUNCH_P(1); break;
+    case 2: LAUNCH_P(2); break;
+    default: LAUNCH_P(4); break;
     }
-    k_cg_calc_p<HOT_ROWS><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal,
-                                                         (int)mode, beta, rev ? 1 : 0, mask);
+#undef LAUNCH_P
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     return TL_OK;
 }
 
 // Fused  p = beta p + r  (cg.cpp:257-281, of iteration t-1)  +  w = A p ; p.w  (cg.cpp:137-195, of
-// iteration t).  48 B/cell instead of 24 + 32: read p, r, kx, ky; write p, w.  The updated p of the
-// one-cell ring around the tile is recomputed from (p, r) of the neighbouring cells -- bit-identical
-// to what the owning tile stores -- with the reflective boundary applied on external faces by index
-// mirroring, so no halo of p or r is read and none has to be exchanged on a single chunk.
+// iteration t).  48 B/cell instead of 24 + 32: read p, r, kx, ky; write p, w.
+// Each thread updates its own two cells of p; the left/right neighbours' updated values come from the
+// adjacent lanes by warp shuffle, only the two edge lanes of a warp recompute them from (p, r) of the
+// neighbouring cell -- bit-identical to what the owning thread stores.  Rows j-1 and j+1 of the
+// updated p slide through registers (the tile's first/last row recomputes the row outside the tile).
+// Reflective boundaries on external faces are applied by index mirroring, so no halo of p is read
+// there; on internal faces the halo of p (old) and r must have been exchanged.
 // Old p is read by neighbouring tiles while this tile overwrites it, so the update is double
-// buffered: reads come from `p_in`, writes go to `p_out` (the chunk's P and SD buffers swap roles).
-template <int ROWS>
+// buffered: reads come from p_in, writes go to p_out (the chunk's P and P2 buffers swap roles).
+template <int U>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out, const double* __restrict__ r,
              const double* __restrict__ kx, const double* __restrict__ ky, double* __restrict__ w,
-             double* __restrict__ d_alphas, RedArgs ra, int first, int rev)
+             double* __restrict__ d_alphas, RedArgs ra, int rows, int rev, int ext_mask)
 {
     DevScal* S = ra.S;
     if (S->conv) return;
-    const double beta = first ? 0.0 : S->beta;
-    const HotTile t = hot_tile<ROWS>(g, rev);
+    const double beta = S->beta;
+    const HotTile t = hot_tile(g, rows, rev);
+    const long pitch = g.pitch;
+    const int lane = threadIdx.x & 31;
+    const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
+    // which neighbours are mirrored (external face at the chunk edge) rather than read
+    const bool mir_l = (ext_mask & 1) && t.kk == klo;
+    const bool mir_r1 = (ext_mask & 2) && t.kk + 1 == khi; // my cell 1 is the last column
+    const bool mir_r0 = (ext_mask & 2) && t.kk == khi;     // my cell 0 is the last column (cell 1 invalid)
+    const bool load_l = t.v0 && !mir_l && lane == 0;
+    // the right neighbour of cell 1 lives in lane+1 unless I am lane 31 or that lane is past the row end
+    const bool load_r = t.v1 && !mir_r1 && (lane == 31 || t.kk + 2 > khi);
+    auto pnew2 = [&](long i) {
+        double2 a = ld2_ro(p_in + i);
+        const double2 b = ld2_ro(r + i);
+        a.x = beta * a.x + b.x;
+        a.y = beta * a.y + b.y;
+        return a;
+    };
+    auto pnew1 = [&](long i) { return beta * __ldg(p_in + i) + __ldg(r + i); };
+    // sides of an updated row held as double2 `c` in every lane
+    auto sides = [&](double2 c, long i, double& l, double& rr) {
+        const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);
+        const double sr = __shfl_down_sync(0xffffffffu, c.x, 1);
+        l = mir_l ? c.x : sl;
+        if (load_l) l = pnew1(i - 1);
+        rr = mir_r1 ? c.y : sr;
+        if (load_r) rr = pnew1(i + 2);
+    };
     double acc[1] = {0.0};
+    long i = t.i;
+    double2 pm = make_double2(0.0, 0.0), pc = pm, kyc = pm;
+    double pl = 0.0, pr = 0.0;
     if (t.v0) {
-        const int pitch = g.pitch;
-        const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
-        // mirrored column offsets for the left / right neighbours of my two cells
-        const int dl = (t.kk - 1 < klo) ? 0 : -1;                 // left neighbour of cell 0
-        const int dr = (t.kk + 2 > khi) ? ((t.kk + 1 > khi) ? 0 : 1) : 2; // right neighbour of cell 1
-        auto pnew2 = [&](long i) {
-            double2 a = ld2_ro(p_in + i);
-            const double2 b = ld2_ro(r + i);
-            if (!first) { a.x = beta * a.x + b.x; a.y = beta * a.y + b.y; }
-            return a;
-        };
-        auto pnew1 = [&](long i) {
-            double a = __ldg(p_in + i);
-            if (!first) a = beta * a + __ldg(r + i);
-            return a;
-        };
-        long i = t.i;
-        const long im = (t.j0 - 1 < jlo) ? i : i - pitch; // reflective: row below the first = itself
-        double2 pm = pnew2(im);
-        double2 pc = pnew2(i);
-        double pl = pnew1(i + dl), pr = pnew1(i + dr);
-        double2 kyc = ld2_ro(ky + i);
-        for (int jj = t.j0; jj < t.j1; ++jj, i += pitch) {
-            const long in = (jj + 1 > jhi) ? i : i + pitch;
-            const double2 pn = pnew2(in);
-            const double pln = pnew1(in + dl), prn = pnew1(in + dr);
-            const double2 kyn = ld2_ro(ky + i + pitch);
-            const double2 kxc = ld2_ro(kx + i);
-            const double kxr = __ldg(kx + i + 2);
-            double2 wv;
-            wv.x = smvp(kxc.x, kxc.y, kyc.x, kyn.x, pc.x, pl, t.v1 ? pc.y : pc.x, pm.x, pn.x);
-            wv.y = smvp(kxc.y, kxr, kyc.y, kyn.y, pc.y, pc.x, pr, pm.y, pn.y);
-            st_pair(w + i, wv, t.v1);
-            st_pair(p_out + i, pc, t.v1);
-            acc[0] += wv.x * pc.x;
-            if (t.v1) acc[0] += wv.y * pc.y;
-            pm = pc; pc = pn; kyc = kyn; pl = pln; pr = prn;
+        pc = pnew2(i);
+        const bool mir_b = (ext_mask & 4) && t.j0 == jlo;
+        pm = mir_b ? pc : pnew2(i - pitch);
+        kyc = ld2_ro(ky + i);
+    }
+    sides(pc, i, pl, pr);
+    for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+        double2 pn[U], kyn[U], kxc[U];
+        double kxr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            pn[u] = make_double2(0.0, 0.0);
+            if (t.v0 && jb + u < t.j1) {
+                const long iu = i + u * pitch;
+                const bool mir_t = (ext_mask & 8) && (jb + u == jhi);
+                if (!mir_t) pn[u] = pnew2(iu + pitch);
+                kyn[u] = ld2_ro(ky + iu + pitch);
+                kxc[u] = ld2_ro(kx + iu);
+                kxr[u] = __ldg(kx + iu + 2);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (jb + u < t.j1) { // warp-uniform
+                const long iu = i + u * pitch;
+                const bool mir_t = (ext_mask & 8) && (jb + u == jhi);
+                if (mir_t) pn[u] = pc;
+                double pln, prn;
+                sides(pn[u], iu + pitch, pln, prn);
+                if (t.v0) {
+                    double2 wv;
+                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, mir_r0 ? pc.x : pc.y, pm.x, pn[u].x);
+                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
+                    st_pair(w + iu, wv, t.v1);
+                    st_pair(p_out + iu, pc, t.v1);
+                    acc[0] += wv.x * pc.x;
+                    if (t.v1) acc[0] += wv.y * pc.y;
+                    pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln; pr = prn;
+                }
+            }
         }
     }
     double tot[1];
@@ -711,15 +866,38 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
         const double alpha = S->rro / tot[0];
         S->alpha = alpha;
         d_alphas[S->iters] = alpha;
-        S->p_pending = 0;
+        S->p_pending = 0; // the pending p update of the previous iteration has now been applied
     }
 }
 
-int tlk_cg_calc_pw(tl_chunk* c, bool first, bool rev)
+// p_in = c->f[P], p_out = c->p2; the caller swaps them after the launch.
+int tlk_cg_calc_pw(tl_chunk* c, bool rev)
 {
-    (void)c; (void)first; (void)rev;
-    tl_set_error("fused p+w kernel is not enabled in this build");
-    return TL_ERR_ARG;
+    const int rows = tile_rows(c, TUNE_PW);
+    dim3 grid = hot_grid(c, rows);
+    TL_TRY(hot_check(c, grid));
+    if (!c->p2) {
+        TL_CUDA(cudaMalloc((void**)&c->p2, c->field_elems * sizeof(double)));
+        TL_CUDA(cudaMemsetAsync(c->p2, 0, c->field_elems * sizeof(double), c->stream));
+    }
+    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    const int mask = external_mask(c);
+#define LAUNCH_PW(U)                                                                                          \
+    k_cg_calc_pw<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],             \
+                                                   c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W],       \
+                                                   c->d_alphas, ra, rows, rev ? 1 : 0, mask)
+    switch (g_batch[TUNE_PW]) {
+    case 1: LAUNCH_PW(1); break;
+    case 2: LAUNCH_PW(2); break;
+    default: LAUNCH_PW(4); break;
+    }
+#undef LAUNCH_PW
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    double* tmp = c->f[TL_FIELD_P];
+    c->f[TL_FIELD_P] = c->p2;
+    c->p2 = tmp;
+    return TL_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

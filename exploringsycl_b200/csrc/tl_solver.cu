@@ -46,7 +46,7 @@ extern "C" void tl_solve_opts_default(tl_solve_opts* o)
     o->error_switch = 0;                // settings.h:32
     o->eps_lim = 1e-5;                  // settings.h:34
     o->check_result = 1;                // settings.h:35
-    o->fuse_p_into_w = 0;
+    o->fuse_p_into_w = 1;               // bit-identical to the three-kernel iteration, 96 instead of 104 B/cell
     o->batch = 0;
 }
 
@@ -108,7 +108,8 @@ __global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test)
     S->conv = (S->iters >= stop_iters) ? 1 : 0;
 }
 
-static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_test, int batch, long* launches)
+static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_test, int batch, long* launches,
+                               bool fused = false)
 {
     k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
     ++g_tl_launches;
@@ -118,15 +119,32 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
     DevScal* snaps[2] = {c->scal_h + 1, c->scal_h + 2};
     cudaEvent_t ev[2] = {c->ev0, c->ev1};
     int enq = c->resident_iters; // iterations already done in this solve
-    int nb = 0;
+    if (fused && enq != 0) {
+        tl_set_error("fused CG iterations must start at iteration 0 of a solve");
+        return TL_ERR_ARG;
+    }
+    int nb = 0, n_pw = 0;
     bool done = (enq >= stop_iters);
     while (!done) {
         const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
         for (int it = 0; it < todo; ++it) {
-            TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false));
-            TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true));
-            TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true));
-            *launches += 3;
+            if (!fused) {
+                // cg_main_step_driver (cg_driver.c:69-124) + the p part of halo_update_driver (:22)
+                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true));
+                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true));
+                *launches += 3;
+            } else {
+                // iteration t >= 1 applies p = beta_{t-1} p + r inside the matvec kernel
+                if (enq + it == 0) {
+                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false));
+                } else {
+                    TL_TRY(tlk_cg_calc_pw(c, false));
+                    ++n_pw;
+                }
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true));
+                *launches += 2;
+            }
         }
         enq += todo;
         TL_CUDA(cudaMemcpyAsync(snaps[nb & 1], c->scal, sizeof(DevScal), cudaMemcpyDeviceToHost, c->stream));
@@ -140,6 +158,19 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
     }
     TL_TRY(tl_fetch_scal(c));
     c->resident_iters = c->scal_h->iters;
+    if (fused) {
+        // Launches enqueued after convergence returned at once, but the host swapped the P/P2
+        // roles for each of them: undo the swaps that did not happen on the device.
+        const int executed_pw = c->scal_h->iters > 0 ? c->scal_h->iters - 1 : 0;
+        if ((n_pw - executed_pw) & 1) {
+            double* tmp = c->f[TL_FIELD_P];
+            c->f[TL_FIELD_P] = c->p2;
+            c->p2 = tmp;
+        }
+        // the last iteration's p update is still pending (cg_driver.c:115) -- apply it, with its halo
+        TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true));
+        *launches += 1;
+    }
     return TL_OK;
 }
 
@@ -165,7 +196,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
     if (!multi) {
         // p's reflective halo is written by calc_p itself; u's halo is only read after the loop
         // (calculate_residual, solve_finished_driver.c:19), so it is refreshed once at the end.
-        TL_TRY(cg_iterate_resident(c, o->max_iters, o->eps, 0, o->batch, &launches));
+        TL_TRY(cg_iterate_resident(c, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w != 0));
         const DevScal* S = c->scal_h;
         error = S->error;
         const bool converged = sqrt(fabs(error)) < o->eps;
@@ -606,18 +637,22 @@ extern "C" int tl_timestep_host(tl_chunk* c, tl_comms* k, const tl_solve_opts* o
 // Kernel micro-benchmark hook (bench.py roofline leg).  Uses the current field contents.
 extern "C" int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_launch)
 {
-    TL_CHECK_ARG(c && ms_per_launch && reps > 0 && which >= 0 && which <= 2, "bad arguments");
+    TL_CHECK_ARG(c && ms_per_launch && reps > 0 && which >= 0 && which <= 3, "bad arguments");
     TL_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
     TL_CUDA(cudaEventCreate(&e0));
     TL_CUDA(cudaEventCreate(&e1));
+    if (which == 3) { // the fused kernel reads beta / conv from the device scalars
+        TL_TRY(tlk_reset_solve_scalars(c, -1.0, 1 << 30));
+    }
     for (int pass = 0; pass < 2; ++pass) { // pass 0 = warm-up
         const int n = pass ? reps : 3;
         if (pass) TL_CUDA(cudaEventRecord(e0, c->stream));
         for (int i = 0; i < n; ++i) {
             if (which == 0) TL_TRY(tlk_cg_calc_w(c, SCAL_IMM, false));
             else if (which == 1) TL_TRY(tlk_cg_calc_ur(c, SCAL_IMM, 1e-9, false));
-            else TL_TRY(tlk_cg_calc_p(c, SCAL_IMM, 0.5, false, false));
+            else if (which == 2) TL_TRY(tlk_cg_calc_p(c, SCAL_IMM, 0.5, false, false));
+            else TL_TRY(tlk_cg_calc_pw(c, false));
         }
         if (pass) TL_CUDA(cudaEventRecord(e1, c->stream));
     }

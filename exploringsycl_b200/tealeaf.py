@@ -77,6 +77,7 @@ class Settings:  # settings.h:64-123 with the defaults of settings.h:15-45
     fields_to_exchange: List[bool] = dc_field(default_factory=lambda: [False] * NUM_FIELDS)
     # extensions of this backend (not in the reference)
     batch: int = 0
+    fuse_p_into_w: bool = True
 
     def reset_fields_to_exchange(self):  # settings.c:64-70
         self.fields_to_exchange = [False] * NUM_FIELDS
@@ -88,6 +89,7 @@ class Settings:  # settings.h:64-123 with the defaults of settings.h:15-45
         o.presteps, o.ppcg_inner_steps = self.presteps, self.ppcg_inner_steps
         o.error_switch, o.eps_lim, o.check_result = int(self.error_switch), self.eps_lim, int(self.check_result)
         o.batch = self.batch
+        o.fuse_p_into_w = int(self.fuse_p_into_w)
         return o
 
 

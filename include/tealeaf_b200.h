@@ -229,8 +229,12 @@ void tl_host_free_pinned(void* p);
 
 /* Kernel micro-benchmark hook used by bench.py's roofline leg: runs `reps` back-to-back launches of
  * one hot kernel on the chunk's stream and returns the average CUDA-event milliseconds per launch.
- * which: 0 cg_calc_w, 1 cg_calc_ur, 2 cg_calc_p, 3 fused p+w. */
+ * which: 0 cg_calc_w, 1 cg_calc_ur, 2 cg_calc_p, 3 fused p+w (overwrites p, w and the solver scalars). */
 int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_launch);
+/* Tuning: rows per tile and rows per load batch (1, 2 or 4) of a hot kernel family
+ * (0 cg_calc_w, 1 cg_calc_ur, 2 cg_calc_p, 3 fused p+w). Results do not depend on `batch`;
+ * reductions depend on `rows` only through the (deterministic) summation order. */
+int tl_set_tuning(int kernel, int rows, int batch);
 long tl_kernel_launch_count(void); /* kernels launched by this library in this process */
 /* CUDA-event timer on the chunk's own stream (torch.cuda.Event only sees torch's stream). */
 int tl_timer_start(tl_chunk* c);

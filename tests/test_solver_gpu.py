@@ -144,3 +144,66 @@ def test_plugin_api_cg_iteration_matches_resident_loop():
     assert tt == a.history[0]["iters_a"]
     assert np.array_equal(a.chunk.read(3)[2:-2, 2:-2], c.read(3)[2:-2, 2:-2])
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("mesh", [(250, 250), (301, 157), (64, 513)])
+def test_fused_p_into_w_is_bit_identical(mesh):
+    """The fused p-update + matvec kernel (48 B/cell instead of 24 + 32) must reproduce the three-kernel
+    iteration bit for bit: same counts, same u / p / r / w fields."""
+    from exploringsycl_b200 import Settings, TeaLeaf, read_config
+    res = []
+    for fused in (False, True):
+        s, states = read_config(os.path.join(DECKS, "tea_250_cg.in"),
+                                Settings(grid_x_cells=mesh[0], grid_y_cells=mesh[1]))
+        s.end_step = 2
+        s.fuse_p_into_w = fused
+        app = TeaLeaf(s, states)
+        summary = app.diffuse()
+        res.append((summary, [h["iters_a"] for h in app.history],
+                    {f: app.chunk.read(f) for f in (3, 4, 7, 8, 2)}))
+        app.close()
+    assert res[0][1] == res[1][1]
+    assert res[0][0] == res[1][0]
+    hd = 2
+    for f in res[0][2]:
+        a, b = res[0][2][f], res[1][2][f]
+        assert np.array_equal(a[hd - 1:-(hd - 1), hd - 1:-(hd - 1)], b[hd - 1:-(hd - 1), hd - 1:-(hd - 1)]), f
+
+
+@pytest.mark.parametrize("rows,batch", [(8, 1), (16, 4), (32, 2)])
+def test_tuning_does_not_change_fields(rows, batch):
+    """Load-batch depth never changes results; rows per tile only reorders the reduction."""
+    from exploringsycl_b200 import TeaLeaf, lib, read_config
+    s, states = read_config(os.path.join(DECKS, "tea_250_cg.in"))
+    s.end_step = 1
+    base = TeaLeaf(s, states)
+    base.diffuse()
+    try:
+        for k in range(4):
+            assert lib().tl_set_tuning(k, rows, batch) == 0
+        s2, states2 = read_config(os.path.join(DECKS, "tea_250_cg.in"))
+        s2.end_step = 1
+        app = TeaLeaf(s2, states2)
+        app.diffuse()
+        assert abs(app.history[0]["iters_a"] - base.history[0]["iters_a"]) <= 1
+        u0, u1 = base.chunk.read(3)[2:-2, 2:-2], app.chunk.read(3)[2:-2, 2:-2]
+        assert np.max(np.abs(u0 - u1)) / np.max(np.abs(u0)) < 1e-12
+        app.close()
+    finally:
+        for k, (r, b) in enumerate(((0, 2), (0, 4), (0, 4), (0, 1))):
+            lib().tl_set_tuning(k, r, b)
+        base.close()
+
+
+def test_bm5_4000_full_deck_matches_reference_goldens():
+    """Benchmark 5 (4000x4000, 10 steps): the reference's own golden (tea.problems) and the thesis'
+    kernel-call count (42297 calls of cg_calc_w / cg_calc_ur, thesis p.26)."""
+    s, summary, hist, u = run_gpu("tea_4000_cg.in")
+    from exploringsycl_b200 import get_checking_value
+    exp = get_checking_value(os.path.join(GOLDEN, "tea_problems.txt"), s)
+    assert abs(100.0 * (summary["temp"] / exp) - 100.0) < 0.001  # field_summary_driver.c:42-43
+    assert rel(summary["temp"], exp) < 2e-11
+    calls = sum(h["total_iters"] for h in hist)
+    assert abs(calls - 42297) <= 10, calls  # +-1 per step from the reduction order
+    assert rel(summary["vol"], 100.0) < 1e-12 and rel(summary["mass"], 8401.6) < 1e-12
+    print("bm5: calls", calls, "temp", repr(summary["temp"]), "iters", [h["iters_a"] for h in hist])
