@@ -82,9 +82,14 @@ void wait_for_requests(Settings* settings, int num_requests, MPI_Request* reques
 {
     START_PROFILING(settings->kernel_profile);
     (void)num_requests; (void)requests;
+    for (size_t ii = 0; ii < g_pending.size(); ++ii) { // all sends first, then all receives
+        const PendingMsg& m = g_pending[ii];
+        if (tl_comms_post(g_comms, m.send, m.len, m.neighbour, m.send_tag) != TL_OK)
+            die(__LINE__, __FILE__, "%s\n", tl_last_error());
+    }
     for (size_t ii = 0; ii < g_pending.size(); ++ii) {
         const PendingMsg& m = g_pending[ii];
-        if (tl_comms_send_recv(g_comms, m.send, m.recv, m.len, m.neighbour, m.send_tag, m.recv_tag) != TL_OK)
+        if (tl_comms_recv(g_comms, m.recv, m.len, m.neighbour, m.recv_tag) != TL_OK)
             die(__LINE__, __FILE__, "%s\n", tl_last_error());
     }
     g_pending.clear();

@@ -92,6 +92,8 @@ SIGNATURES = {
     "tl_comms_sum": ([_vp, _pd], _i),
     "tl_comms_min": ([_vp, _pd], _i),
     "tl_comms_send_recv": ([_vp, _dp, _dp, _i, _i, _i, _i], _i),
+    "tl_comms_post": ([_vp, _dp, _i, _i, _i], _i),
+    "tl_comms_recv": ([_vp, _dp, _i, _i, _i], _i),
     "tl_comms_attach_chunk": ([_vp, _vp], _i),
     "tl_decompose": ([_i, _i, _i, _i, _pi, _pi, _pi, _pi, _i4, _pi, _pi], _i),
     "tl_halo_update": ([_vp, _vp, _i6, _i], _i),

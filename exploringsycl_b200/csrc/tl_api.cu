@@ -71,8 +71,13 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
     g.y = ny + 2 * halo_depth;
     g.pitch = (g.x + 15) / 16 * 16;
     g.off = (16 - halo_depth % 16) % 16;
-    c->field_elems = (size_t)g.off + (size_t)g.y * g.pitch + 64;
-    for (int f = 0; f < TL_NUM_FIELDS; ++f) TL_TRY(dev_zalloc(&c->f[f], c->field_elems));
+    c->field_elems = ((size_t)g.off + (size_t)g.y * g.pitch + 64 + 31) / 32 * 32; // 256-byte multiple
+    // One slab for all fields, a 2 MiB multiple: it is its own allocation block, so one CUDA-IPC handle
+    // maps every field of this chunk into the neighbouring ranks (tl_comms_attach_chunk).
+    c->slab_bytes = (c->field_elems * sizeof(double) * TL_NUM_FIELDS + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    TL_CUDA(cudaMalloc((void**)&c->slab, c->slab_bytes));
+    TL_CUDA(cudaMemset(c->slab, 0, c->slab_bytes));
+    for (int f = 0; f < TL_NUM_FIELDS; ++f) c->f[f] = c->slab + (size_t)f * c->field_elems;
     TL_TRY(dev_zalloc(&c->cell_x, g.x + 2));
     TL_TRY(dev_zalloc(&c->cell_y, g.y + 2));
     TL_TRY(dev_zalloc(&c->vertex_x, g.x + 2));
@@ -111,8 +116,8 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     if (!c) return TL_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int f = 0; f < TL_NUM_FIELDS; ++f) cudaFree(c->f[f]);
-    if (c->p2) cudaFree(c->p2);
+    cudaFree(c->slab);
+    if (c->p2_alloc) cudaFree(c->p2_alloc);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->scal); cudaFreeHost(c->scal_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas); cudaFree(c->d_cheby);

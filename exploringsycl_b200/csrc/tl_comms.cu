@@ -44,8 +44,12 @@ struct ShmHeader {
     std::atomic<int> nb_list[TLC_MAX_RANKS][4]; // neighbour ranks each rank sends to (registered lazily)
     // GPU arenas
     cudaIpcMemHandle_t arena[TLC_MAX_RANKS];
+    cudaIpcMemHandle_t pfield[TLC_MAX_RANKS]; // each rank's field slab (resident CG loop stores halos into p)
+    unsigned long long arena_off[TLC_MAX_RANKS];  // byte offset of the arena / p field inside the shared block:
+    unsigned long long pfield_off[TLC_MAX_RANKS]; // cudaIpcOpenMemHandle maps the BASE of the allocation block
     unsigned long long arena_face_elems[TLC_MAX_RANKS];
     int arena_device[TLC_MAX_RANKS];
+    int geo[TLC_MAX_RANKS][4];                // x, y, pitch, off of each rank's chunk
 };
 
 struct tl_comms {
@@ -61,7 +65,11 @@ struct tl_comms {
     size_t arena_bytes;
     size_t face_elems;  // common (max over ranks) per-face capacity in doubles
     void* peer_arena[TLC_MAX_RANKS];
+    void* peer_pfield[TLC_MAX_RANKS];
+    void* peer_arena_base[TLC_MAX_RANKS];  // what cudaIpcOpenMemHandle returned (to close)
+    void* peer_pfield_base[TLC_MAX_RANKS];
     unsigned long long xchg_seq; // exchange phases completed
+    unsigned long long res_seq;  // resident-loop iterations launched so far (slot / halo flag base)
 };
 
 static double now_s()
@@ -71,7 +79,7 @@ static double now_s()
     return ts.tv_sec + 1e-9 * ts.tv_nsec;
 }
 
-static const double TLC_TIMEOUT_S = 120.0;
+static const double TLC_TIMEOUT_S = 60.0;
 
 #define SPIN_UNTIL(cond, what)                                              \
     do {                                                                    \
@@ -157,7 +165,10 @@ extern "C" int tl_comms_destroy(tl_comms* k)
     if (!k) return TL_OK;
     if (!k->host_only) {
         for (int r = 0; r < k->num_ranks; ++r)
-            if (k->peer_arena[r] && r != k->rank) cudaIpcCloseMemHandle(k->peer_arena[r]);
+            if (r != k->rank) {
+                if (k->peer_arena_base[r]) cudaIpcCloseMemHandle(k->peer_arena_base[r]);
+                if (k->peer_pfield_base[r]) cudaIpcCloseMemHandle(k->peer_pfield_base[r]);
+            }
     }
     tl_comms_barrier(k);
     if (k->arena) cudaFree(k->arena);
@@ -222,13 +233,15 @@ static int nb_index(tl_comms* k, int src, int dst, bool create)
     return -1;
 }
 
-// send_recv_message + wait_for_requests, comms.c:31-52, on host buffers.
-extern "C" int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double* recv_buffer, int buffer_len,
-                                  int neighbour, int send_tag, int recv_tag)
+// send_recv_message + wait_for_requests, comms.c:31-52, on host buffers.  tl_comms_post is the
+// MPI_Isend half (copies the message into this rank's mailbox for `neighbour`), tl_comms_recv the
+// MPI_Irecv + MPI_Wait half.  Posting every message of a phase before receiving any keeps the
+// exchange free of rank-to-rank chains.
+extern "C" int tl_comms_post(tl_comms* k, const double* send_buffer, int buffer_len, int neighbour, int send_tag)
 {
-    TL_CHECK_ARG(k && send_buffer && recv_buffer && buffer_len >= 0 && buffer_len <= TLC_SLOT_DOUBLES &&
-                     neighbour >= 0 && neighbour < k->num_ranks && neighbour != k->rank &&
-                     (send_tag == 0 || send_tag == 1) && (recv_tag == 0 || recv_tag == 1), "bad arguments");
+    TL_CHECK_ARG(k && send_buffer && buffer_len >= 0 && buffer_len <= TLC_SLOT_DOUBLES && neighbour >= 0 &&
+                     neighbour < k->num_ranks && neighbour != k->rank && (send_tag == 0 || send_tag == 1),
+                 "bad arguments");
     const int si = nb_index(k, k->rank, neighbour, true);
     TL_CHECK_ARG(si >= 0, "more than 4 neighbours");
     Mailbox* sb = &k->boxes[((size_t)k->rank * 4 + si) * 2 + send_tag];
@@ -237,6 +250,13 @@ extern "C" int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double
     memcpy(sb->data, send_buffer, sizeof(double) * (size_t)buffer_len);
     sb->len = buffer_len;
     sb->seq_w.fetch_add(1, std::memory_order_release);
+    return TL_OK;
+}
+
+extern "C" int tl_comms_recv(tl_comms* k, double* recv_buffer, int buffer_len, int neighbour, int recv_tag)
+{
+    TL_CHECK_ARG(k && recv_buffer && buffer_len >= 0 && neighbour >= 0 && neighbour < k->num_ranks &&
+                     neighbour != k->rank && (recv_tag == 0 || recv_tag == 1), "bad arguments");
     int ri = -1;
     SPIN_UNTIL((ri = nb_index(k, neighbour, k->rank, false)) >= 0, "neighbour to post");
     Mailbox* rb = &k->boxes[((size_t)neighbour * 4 + ri) * 2 + recv_tag];
@@ -249,6 +269,13 @@ extern "C" int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double
     memcpy(recv_buffer, rb->data, sizeof(double) * (size_t)buffer_len);
     rb->seq_r.fetch_add(1, std::memory_order_release);
     return TL_OK;
+}
+
+extern "C" int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double* recv_buffer, int buffer_len,
+                                  int neighbour, int send_tag, int recv_tag)
+{
+    TL_TRY(tl_comms_post(k, send_buffer, buffer_len, neighbour, send_tag));
+    return tl_comms_recv(k, recv_buffer, buffer_len, neighbour, recv_tag);
 }
 
 // initialise.c:34-134, for chunk == rank (one chunk per rank)
@@ -301,14 +328,48 @@ extern "C" int tl_decompose(int grid_x_cells, int grid_y_cells, int num_chunks, 
 // ---------------------------------------------------------------------------------------------
 // GPU peer path
 // ---------------------------------------------------------------------------------------------
-// Arena layout (identical on every rank, sized with the max face capacity over ranks):
-//   recv[face 0..3][parity 0..1][face_elems] doubles | flags[4] u64 | red slots [2][8] doubles | red flags [2][8] u64
+// cudaMalloc may sub-allocate from a larger block and CUDA IPC shares the whole block: the opener gets the
+// block base.  Offsets are taken with cuMemGetAddressRange (fetched at run time: no link-time libcuda
+// dependency, so the library still loads on CPU-only machines).
+static int block_offset(const void* ptr, unsigned long long* off)
+{
+    typedef int (*range_fn)(unsigned long long*, size_t*, unsigned long long);
+    static range_fn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &sym, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || !sym) {
+            tl_set_error("cudaGetDriverEntryPoint(cuMemGetAddressRange) failed");
+            return TL_ERR_CUDA;
+        }
+        fn = (range_fn)sym;
+    }
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (fn(&base, &size, (unsigned long long)ptr) != 0) {
+        tl_set_error("cuMemGetAddressRange failed");
+        return TL_ERR_CUDA;
+    }
+    *off = (unsigned long long)ptr - base;
+    return TL_OK;
+}
+
+// Arena layout (identical on every rank, sized with the max face capacity over ranks), in doubles:
+//   recv[face 0..3][parity 0..1][face_elems] | tail:
+//   tail+0..3   flags of the generic halo exchange (by receiving face)
+//   tail+4..7   p-halo flags of the resident CG loop (by receiving face)
+//   tail+8..39  reduction slots  [kind][parity][rank]
+//   tail+40..71 reduction flags  [kind][parity][rank]
 static size_t arena_recv_off(const tl_comms* k, int face, int parity)
 {
     return ((size_t)face * 2 + parity) * k->face_elems;
 }
 static size_t arena_flags_off(const tl_comms* k) { return (size_t)8 * k->face_elems; }
-static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 4 + 2 * TL_MAX_PEERS * 2; }
+static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 128; }
+#define ARENA_HFLAGS 4
+#define ARENA_SLOTS 8
+#define ARENA_SFLAGS 40
 
 extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
 {
@@ -319,42 +380,93 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
     ShmHeader* h = k->hdr;
     h->arena_face_elems[k->rank] = c->face_elems;
     h->arena_device[k->rank] = c->device;
+    h->geo[k->rank][0] = c->g.x;
+    h->geo[k->rank][1] = c->g.y;
+    h->geo[k->rank][2] = c->g.pitch;
+    h->geo[k->rank][3] = c->g.off;
     TL_TRY(tl_comms_barrier(k));
     size_t fe = 0;
     for (int r = 0; r < k->num_ranks; ++r) fe = h->arena_face_elems[r] > fe ? h->arena_face_elems[r] : fe;
     k->face_elems = fe;
-    k->arena_bytes = arena_total(k) * sizeof(double);
+    k->arena_bytes = (arena_total(k) * sizeof(double) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
     TL_CUDA(cudaMalloc((void**)&k->arena, k->arena_bytes));
     TL_CUDA(cudaMemset(k->arena, 0, k->arena_bytes));
     TL_CUDA(cudaDeviceSynchronize());
     TL_CUDA(cudaIpcGetMemHandle(&h->arena[k->rank], k->arena));
+    TL_CUDA(cudaIpcGetMemHandle(&h->pfield[k->rank], c->slab));
+    {
+        unsigned long long o1 = 0, o2 = 0;
+        TL_TRY(block_offset(k->arena, &o1));
+        TL_TRY(block_offset(c->slab, &o2));
+        h->arena_off[k->rank] = o1;
+        h->pfield_off[k->rank] = o2 + (unsigned long long)((char*)(c->slab + (size_t)TL_FIELD_P * c->field_elems) - (char*)c->slab);
+    }
     std::atomic_thread_fence(std::memory_order_release);
     TL_TRY(tl_comms_barrier(k));
     std::atomic_thread_fence(std::memory_order_acquire);
     k->peer_arena[k->rank] = k->arena;
-    for (int f = 0; f < 4; ++f) {
-        const int n = c->nb[f];
-        if (n == TL_EXTERNAL_FACE || k->peer_arena[n]) continue;
-        cudaError_t e = cudaIpcOpenMemHandle(&k->peer_arena[n], h->arena[n], cudaIpcMemLazyEnablePeerAccess);
+    // the reduction slots live on every rank: map all arenas; p fields only of the neighbours
+    for (int r = 0; r < k->num_ranks; ++r) {
+        if (r == k->rank || k->peer_arena[r]) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&k->peer_arena[r], h->arena[r], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
-            tl_set_error("cudaIpcOpenMemHandle(rank %d -> %d) failed: %s", k->rank, n, cudaGetErrorString(e));
+            tl_set_error("cudaIpcOpenMemHandle(arena, rank %d -> %d) failed: %s", k->rank, r, cudaGetErrorString(e));
             return TL_ERR_COMMS;
         }
+        k->peer_arena_base[r] = k->peer_arena[r];
+        k->peer_arena[r] = (char*)k->peer_arena[r] + h->arena_off[r];
     }
-    static const int opposite[4] = {TL_FACE_RIGHT, TL_FACE_LEFT, TL_FACE_TOP, TL_FACE_BOTTOM};
     for (int f = 0; f < 4; ++f) {
         const int n = c->nb[f];
-        c->peers.nb_recv[f] = nullptr;
-        c->peers.nb_flag[f] = nullptr;
+        if (n == TL_EXTERNAL_FACE || k->peer_pfield[n]) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&k->peer_pfield[n], h->pfield[n], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            tl_set_error("cudaIpcOpenMemHandle(p field, rank %d -> %d) failed: %s", k->rank, n, cudaGetErrorString(e));
+            return TL_ERR_COMMS;
+        }
+        k->peer_pfield_base[n] = k->peer_pfield[n];
+        k->peer_pfield[n] = (char*)k->peer_pfield[n] + h->pfield_off[n];
+    }
+    static const int opposite[4] = {TL_FACE_RIGHT, TL_FACE_LEFT, TL_FACE_TOP, TL_FACE_BOTTOM};
+    MultiCtx& mc = c->mc;
+    memset(&mc, 0, sizeof(mc));
+    mc.num_ranks = k->num_ranks;
+    mc.rank = k->rank;
+    double* tail = k->arena + arena_flags_off(k);
+    mc.slots_local = tail + ARENA_SLOTS;
+    mc.sflags_local = (unsigned long long*)(tail + ARENA_SFLAGS);
+    mc.hflags_local = (unsigned long long*)(tail + ARENA_HFLAGS);
+    for (int r = 0; r < k->num_ranks; ++r) {
+        double* ptail = (double*)k->peer_arena[r] + arena_flags_off(k);
+        mc.slots_peer[r] = ptail + ARENA_SLOTS;
+        mc.sflags_peer[r] = (unsigned long long*)(ptail + ARENA_SFLAGS);
+    }
+    for (int f = 0; f < 4; ++f) {
+        const int n = c->nb[f];
+        c->nb_recv[f] = nullptr;
+        c->nb_flag[f] = nullptr;
         if (n == TL_EXTERNAL_FACE) continue;
         double* base = (double*)k->peer_arena[n];
-        c->peers.nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
-        c->peers.nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
+        c->nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
+        c->nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
+        mc.nb_p[f] = (double*)k->peer_pfield[n];
+        mc.nb_hflag[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_HFLAGS) + opposite[f];
+        mc.nb_x[f] = h->geo[n][0];
+        mc.nb_y[f] = h->geo[n][1];
+        mc.nb_pitch[f] = h->geo[n][2];
+        mc.nb_off[f] = h->geo[n][3];
     }
-    c->peers.rank = k->rank;
-    c->peers.num_ranks = k->num_ranks;
     c->has_peers = true;
     return tl_comms_barrier(k);
+}
+
+// Sequence bases of the resident loop: every rank launches the same iterations in the same order, so
+// a per-endpoint counter stays in lockstep across ranks.
+unsigned long long tlc_resident_seq_advance(tl_comms* k, int launched)
+{
+    const unsigned long long base = k->res_seq;
+    k->res_seq += (unsigned long long)launched;
+    return base;
 }
 
 __global__ void k_signal(unsigned long long* remote_flag, unsigned long long v)
@@ -370,7 +482,7 @@ __global__ void k_wait(unsigned long long* flag, unsigned long long v, DevScal* 
     for (;;) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
         if (cur >= v) break;
-        if (clock64() - t0 > 40000000000LL) { // ~20 s: give up rather than hang the GPU
+        if (clock64() - t0 > 10000000000LL) { // ~5 s: give up rather than hang the GPU
             S->pad = 0xdeadu;
             break;
         }
@@ -396,8 +508,8 @@ int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth)
         for (int f = f0; f < f0 + 2; ++f) {
             if (c->nb[f] == TL_EXTERNAL_FACE) continue;
             int len = 0;
-            TL_TRY(tlk_pack_face(c, fields, depth, f, true, c->peers.nb_recv[f] + (size_t)par * k->face_elems, &len));
-            k_signal<<<1, 1, 0, c->stream>>>(c->peers.nb_flag[f], seq);
+            TL_TRY(tlk_pack_face(c, fields, depth, f, true, c->nb_recv[f] + (size_t)par * k->face_elems, &len));
+            k_signal<<<1, 1, 0, c->stream>>>(c->nb_flag[f], seq);
             ++g_tl_launches;
         }
         for (int f = f0; f < f0 + 2; ++f) {

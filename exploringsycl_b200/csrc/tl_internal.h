@@ -28,26 +28,44 @@ struct Geo {
 // kernels, read by the head of the next kernel: alpha/beta never visit the host inside a solve.
 struct DevScal {
     double rro, pw, rrn, alpha, beta, error, bb, eps;
+    double rro_par[2]; // multi-rank loop: rro of iteration t lives in rro_par[t & 1] (written one kernel earlier)
     double sums[8];
     int iters;         // CG iterations completed in this solve
     int conv;          // set when sqrt(|rrn|) < eps (cg_driver.c:24)
     int p_pending;     // calc_ur ran: the matching calc_p must still run
     int max_iters;
+    int conv_iter;     // multi-rank loop: iterations >= conv_iter are no-ops (INT_MAX while running)
     int conv_mode;     // 0: sqrt(|rrn|) < eps (cg_driver.c:24); 1: |rrn| < eps (cheby_driver.c:70)
     unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
     unsigned int seq;        // reduction sequence number (multi-GPU slot parity)
-    unsigned int pad;
+    unsigned int pad;        // 0xdead: a peer wait timed out
+    unsigned long long dbg[4]; // first timed-out wait: site, wanted value, seen value, block id
 };
 
-// Peer tables for the NVLink path (filled by tl_comms_attach_chunk).
-struct PeerTable {
-    int rank, num_ranks;
-    // scalar all-reduce slots: slots[parity][src_rank] on every rank; peers write, owner reads.
-    double* slot_base[TL_MAX_PEERS];            // peer-mapped pointer to rank r's slot array
-    unsigned long long* flag_base[TL_MAX_PEERS]; // peer-mapped pointer to rank r's flag array
-    // halo staging: recv buffers of the 4 neighbours (peer-mapped), indexed by my face
-    double* nb_recv[4];
-    unsigned long long* nb_flag[4];
+// Multi-rank context of the resident CG loop (passed by value to the hot kernels; num_ranks == 1
+// selects the single-GPU behaviour).  All peer pointers are CUDA-IPC mappings of the other ranks'
+// HBM: stores to them travel over NVLink / NVSwitch.
+//   slots : [kind 0 = p.w, 1 = r.r][parity][source rank] partial sums, one copy on EVERY rank.  The
+//           tail CTA of a reduction kernel stores its rank's partial into all ranks' copies and then
+//           releases a sequence flag; the head of the consumer kernel acquires the N flags and adds
+//           the N partials in rank order (bit-identical on every rank, same order as tl_comms_sum).
+//   halo  : calc_p stores its edge cells straight into the neighbour's halo cells of p; the last CTA
+//           to finish releases a per-face flag that the neighbour's edge tiles of calc_w acquire.
+#define TL_SLOT_IDX(kind, par, r) (((kind) * 2 + (par)) * TL_MAX_PEERS + (r))
+struct MultiCtx {
+    int num_ranks, rank;
+    int tl;                       // iteration index local to this resident call
+    int it_global;                // iteration index within the solve (cg_alphas / cg_betas index)
+    unsigned long long sbase;     // slot flag value of local iteration tl is sbase + tl + 1
+    unsigned long long hbase;     // halo flag value written after calc_p of local iteration tl is hbase + tl + 1
+    double* slots_local;
+    unsigned long long* sflags_local;
+    unsigned long long* hflags_local; // [4] by my face
+    double* slots_peer[TL_MAX_PEERS];
+    unsigned long long* sflags_peer[TL_MAX_PEERS];
+    double* nb_p[4];              // neighbour's p field base (peer-mapped), by my face; null if external
+    unsigned long long* nb_hflag[4]; // neighbour's halo flag of the opposite face
+    int nb_pitch[4], nb_x[4], nb_y[4], nb_off[4];
 };
 
 struct tl_chunk {
@@ -58,9 +76,12 @@ struct tl_chunk {
     int nb[4];
     int left, bottom;
     size_t field_elems;           // allocated doubles per 2-D field
-    double* f[TL_NUM_FIELDS];     // device
+    double* slab;                 // one allocation holding all 2-D fields (IPC-shared with neighbours)
+    size_t slab_bytes;
+    double* f[TL_NUM_FIELDS];     // device, slab + f * field_elems (P may point to p2 in fused mode)
     double *cell_x, *cell_y, *vertex_x, *vertex_y; // device 1-D
     double* p2;                   // device, second p buffer of the fused p+w kernel (lazily allocated)
+    double* p2_alloc;             // the allocation behind it (P and P2 swap roles; this is what gets freed)
     double* partials;             // device, per-tile partial sums (4 lanes)
     int partial_cap;              // tiles
     DevScal* scal;                // device
@@ -79,7 +100,9 @@ struct tl_chunk {
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     tl_comms* comms;              // non-null once attached
-    PeerTable peers;
+    MultiCtx mc;                  // template filled by tl_comms_attach_chunk (tl/it_global/sbase/hbase per launch)
+    double* nb_recv[4];           // neighbours' receive buffers of the generic halo exchange (peer-mapped)
+    unsigned long long* nb_flag[4];
     bool has_peers;
     int resident_iters;           // CG iterations enqueued so far in the current solve (host bookkeeping)
 };
@@ -122,9 +145,9 @@ int tlk_field_summary(tl_chunk* c);                       // -> scal->sums[0..3]
 int tlk_local_halos(tl_chunk* c, const int fields[6], int depth);
 int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len);
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
-int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev);                // -> scal->pw (& alpha when SCAL_DEV)
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev); // -> scal->rrn (& beta, conv when SCAL_DEV)
-int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo);
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr);                // -> scal->pw (& alpha when SCAL_DEV)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr); // -> scal->rrn (& beta, conv when SCAL_DEV)
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc = nullptr);
 int tlk_cg_calc_pw(tl_chunk* c, bool rev);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);

@@ -417,11 +417,14 @@ __global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
     S->eps = eps;
     S->iters = 0;
     S->conv = 0;
+    S->conv_iter = 0x7fffffff;
     S->p_pending = 0;
     S->max_iters = max_iters;
     S->conv_mode = 0;
     S->pad = 0u;
+    S->dbg[0] = S->dbg[1] = S->dbg[2] = S->dbg[3] = 0ull;
     S->counter[0] = 0u;
+    S->counter[1] = 0u;
 }
 int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
 {
@@ -430,6 +433,82 @@ int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multi-rank helpers of the resident CG loop (see MultiCtx in tl_internal.h)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *flag >= want.  Bounded (~20 s) so that a lost peer cannot hang the GPU: on timeout an
+// error mark is left in DevScal.pad and the caller carries on with whatever is there.
+__device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
+                                          unsigned long long site = 0)
+{
+    const long long t0 = clock64();
+    unsigned long long seen;
+    while ((seen = ld_acquire_sys(flag)) < want) {
+        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
+        if (clock64() - t0 > 4000000000LL) { // ~2 s
+            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
+                S->dbg[0] = site;
+                S->dbg[1] = want;
+                S->dbg[2] = seen;
+                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
+            }
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+// Sum of the N ranks' partials of (kind, local iteration tl) in rank order; waits for their flags
+// when `wait` (the partials of an earlier iteration are already complete).
+__device__ __forceinline__ double mc_sum(const MultiCtx& mc, int kind, int tl, bool wait, DevScal* S)
+{
+    const int par = tl & 1;
+    double s = 0.0;
+    for (int r = 0; r < mc.num_ranks; ++r) {
+        const int idx = TL_SLOT_IDX(kind, par, r);
+        if (wait) spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
+                            1000ull + 100ull * kind + 10ull * r + (unsigned long long)tl * 100000ull);
+        const double v = ld_volatile_f64(mc.slots_local + idx);
+        s = (r == 0) ? v : s + v;
+    }
+    return s;
+}
+// Tail of a reduction kernel: this rank's partial goes to every rank's slot, then the flag.
+__device__ __forceinline__ void mc_publish(const MultiCtx& mc, int kind, double partial)
+{
+    const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
+    for (int r = 0; r < mc.num_ranks; ++r) mc.slots_peer[r][idx] = partial;
+    __threadfence_system();
+    for (int r = 0; r < mc.num_ranks; ++r)
+        st_release_sys(mc.sflags_peer[r] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
+}
+__device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
+{
+    return S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
+}
+// Head of every multi-rank kernel: is this launch a no-op?  Once calc_p of iteration X has seen
+// convergence it stamps conv_iter = X + 1; every later launch returns at once.  (One HBM-resident
+// scalar written in an earlier kernel: no peer traffic, no slot reads on this path.)
+__device__ __forceinline__ bool mc_skip(const MultiCtx& mc, const DevScal* S)
+{
+    return mc.it_global >= *(volatile const int*)&S->conv_iter;
 }
 
 // Hot-kernel tile: TL_TPB threads x 2 columns, `rows` rows.  kk is the first of the thread's two
@@ -501,16 +580,36 @@ static int hot_check(const tl_chunk* c, dim3 grid)
 // cg.cpp:137-195 cg_calc_w:  w = A p (5-point SMVP) fused with the p.w dot product.
 // 32 B/cell of HBM traffic: read p, kx, ky; write w.  Rows j-1, j, j+1 of p and rows j, j+1 of ky
 // slide through registers, so every element is requested from L2 once per tile.
-template <int U>
+template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, const double* __restrict__ ky,
-            double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev)
+            double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev,
+            const MultiCtx mc)
 {
     DevScal* S = ra.S;
-    if (mode == SCAL_DEV) {
+    constexpr bool multi = MULTI;
+    if (mode == SCAL_DEV && !multi) {
         const int conv = S->conv;
         if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S->p_pending = 0;
         if (conv) return;
+    }
+    if constexpr (MULTI) {
+        // converged already?  edge tiles: has the neighbour's calc_p delivered this iteration's halo of p?
+        __shared__ int s_skip;
+        if (threadIdx.x == 0) {
+            s_skip = mc_skip(mc, S) ? 1 : 0;
+            if (!s_skip && mc.tl > 0) {
+                const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+                const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+                const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
+                if (bx == 0 && mc.nb_p[TL_FACE_LEFT]) spin_flag(mc.hflags_local + TL_FACE_LEFT, want, S, 1ull + (unsigned long long)mc.tl * 100000ull);
+                if (bx == gridDim.x - 1 && mc.nb_p[TL_FACE_RIGHT]) spin_flag(mc.hflags_local + TL_FACE_RIGHT, want, S, 2ull + (unsigned long long)mc.tl * 100000ull);
+                if (by == 0 && mc.nb_p[TL_FACE_BOTTOM]) spin_flag(mc.hflags_local + TL_FACE_BOTTOM, want, S, 3ull + (unsigned long long)mc.tl * 100000ull);
+                if (by == gridDim.y - 1 && mc.nb_p[TL_FACE_TOP]) spin_flag(mc.hflags_local + TL_FACE_TOP, want, S, 4ull + (unsigned long long)mc.tl * 100000ull);
+            }
+        }
+        __syncthreads();
+        if (s_skip) return;
     }
     const HotTile t = hot_tile(g, rows, rev);
     double acc[1] = {0.0};
@@ -553,7 +652,9 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
         S->pw = tot[0];
-        if (mode == SCAL_DEV) {
+        if (multi) {
+            mc_publish(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
+        } else if (mode == SCAL_DEV) {
             const double alpha = S->rro / tot[0]; // cg_driver.c:87
             S->alpha = alpha;
             d_alphas[S->iters] = alpha;           // cg_driver.c:93
@@ -561,15 +662,23 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
     }
 }
 
-int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev)
+static const MultiCtx g_single_ctx = {1};
+
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc)
 {
     const int rows = tile_rows(c, TUNE_W);
     dim3 grid = hot_grid(c, rows);
     TL_TRY(hot_check(c, grid));
     RedArgs ra{c->partials, c->partial_cap, c->scal};
 #define LAUNCH_W(U)                                                                                          \
-    k_cg_calc_w<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], \
-                                                  c->f[TL_FIELD_W], c->d_alphas, ra, (int)mode, rows, rev ? 1 : 0)
+    if (mc && mc->num_ranks > 1)                                                                             \
+        k_cg_calc_w<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],          \
+                                                            c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, \
+                                                            (int)mode, rows, rev ? 1 : 0, *mc);                  \
+    else                                                                                                     \
+        k_cg_calc_w<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],         \
+                                                             c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, \
+                                                             (int)mode, rows, rev ? 1 : 0, g_single_ctx)
     switch (g_batch[TUNE_W]) {
     case 1: LAUNCH_W(1); break;
     case 2: LAUNCH_W(2); break;
@@ -583,35 +692,62 @@ int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev)
 
 // cg.cpp:198-254 cg_calc_ur:  u += alpha p ; r -= alpha w ; fused with the r.r reduction.
 // 48 B/cell: read u, p, r, w; write u, r.
-template <int U>
+template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double* __restrict__ p,
              const double* __restrict__ w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
-             int rows, int rev)
+             int rows, int rev, double* __restrict__ d_alphas, const MultiCtx mc)
 {
     DevScal* S = ra.S;
+    constexpr bool multi = MULTI;
     double alpha = alpha_imm;
-    if (mode == SCAL_DEV) {
+    if (mode == SCAL_DEV && !multi) {
         if (S->conv) return;
         alpha = S->alpha;
     }
     const HotTile t = hot_tile(g, rows, rev);
+    const long pitch = g.pitch;
     double acc[1] = {0.0};
-    if (t.v0) {
-        long i = t.i;
-        const long pitch = g.pitch;
-        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-            double2 uv[U], rv[U], pv[U], wv[U];
+    long i = t.i;
+    double2 uv[U], rv[U], pv[U], wv[U];
+    auto load_batch = [&](int jb) {
 #pragma unroll
-            for (int q = 0; q < U; ++q) {
-                if (jb + q < t.j1) {
-                    const long iq = i + q * pitch;
-                    uv[q] = ld2(u + iq);
-                    rv[q] = ld2(r + iq);
-                    pv[q] = ld2_ro(p + iq);
-                    wv[q] = ld2_ro(w + iq);
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                const long iq = i + q * pitch;
+                uv[q] = ld2(u + iq);
+                rv[q] = ld2(r + iq);
+                pv[q] = ld2_ro(p + iq);
+                wv[q] = ld2_ro(w + iq);
+            }
+        }
+    };
+    // The first batch of loads does not depend on alpha: it is issued BEFORE the multi-rank head, so the
+    // wait for the peers' p.w partials overlaps with this tile's HBM latency.
+    if constexpr (MULTI) {
+        if (t.v0) load_batch(t.j0);
+        __shared__ int s_skip;
+        __shared__ double s_alpha;
+        if (threadIdx.x == 0) {
+            s_skip = mc_skip(mc, S) ? 1 : 0;
+            if (!s_skip) {
+                const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
+                const double pw = mc_sum(mc, 0, mc.tl, true, S); // all ranks' p.w, rank order
+                s_alpha = rro / pw;                               // cg_driver.c:87
+                if (blockIdx.x == 0 && blockIdx.y == 0) {
+                    S->pw = pw;
+                    S->alpha = s_alpha;
+                    d_alphas[mc.it_global] = s_alpha;             // cg_driver.c:93
                 }
             }
+        }
+        __syncthreads();
+        if (s_skip) return;
+        alpha = s_alpha;
+    }
+    if (t.v0) {
+        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+            if (!MULTI || jb != t.j0) load_batch(jb);
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 if (jb + q < t.j1) {
@@ -631,7 +767,9 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
         S->rrn = tot[0];
-        if (mode == SCAL_DEV) {
+        if (multi) {
+            mc_publish(mc, 1, tot[0]); // sum_over_ranks(rrn), cg_driver.c:104, over NVLink
+        } else if (mode == SCAL_DEV) {
             const double rrn = tot[0];
             const double beta = rrn / S->rro; // cg_driver.c:106
             S->beta = beta;
@@ -646,16 +784,23 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
     }
 }
 
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc)
 {
     const int rows = tile_rows(c, TUNE_UR);
     dim3 grid = hot_grid(c, rows);
     TL_TRY(hot_check(c, grid));
     RedArgs ra{c->partials, c->partial_cap, c->scal};
 #define LAUNCH_UR(U)                                                                                       \
-    k_cg_calc_ur<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R], c->f[TL_FIELD_P], \
-                                                   c->f[TL_FIELD_W], c->d_betas, ra, (int)mode, alpha, rows,    \
-                                                   rev ? 1 : 0)
+    if (mc && mc->num_ranks > 1)                                                                           \
+        k_cg_calc_ur<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],        \
+                                                             c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra, \
+                                                             (int)mode, alpha, rows, rev ? 1 : 0, c->d_alphas, \
+                                                             *mc);                                             \
+    else                                                                                                   \
+        k_cg_calc_ur<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],       \
+                                                              c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas,  \
+                                                              ra, (int)mode, alpha, rows, rev ? 1 : 0,          \
+                                                              c->d_alphas, g_single_ctx)
     switch (g_batch[TUNE_UR]) {
     case 1: LAUNCH_UR(1); break;
     case 2: LAUNCH_UR(2); break;
@@ -693,27 +838,53 @@ __device__ __forceinline__ void p_halo_store(const Geo& g, double* p, long i, in
     }
 }
 
+// Multi-rank: the thread that owns an edge cell of an INTERNAL face stores the updated p straight into
+// the neighbour's halo cell over NVLink (what pack -> MPI -> unpack does in remote_halo_driver.c for
+// depth 1; the 5-point stencil never reads halo corners, so none are sent).
+__device__ __forceinline__ void p_remote_store(const Geo& g, const MultiCtx& mc, int jj, double2 pv, const HotTile& t)
+{
+    const int last = g.x - g.hd - 1;
+    if (mc.nb_p[TL_FACE_LEFT] && t.kk == g.hd) // my first column -> left neighbour's right halo column
+        mc.nb_p[TL_FACE_LEFT][(long)mc.nb_off[TL_FACE_LEFT] + (long)jj * mc.nb_pitch[TL_FACE_LEFT] +
+                              (mc.nb_x[TL_FACE_LEFT] - g.hd)] = pv.x;
+    if (mc.nb_p[TL_FACE_RIGHT]) { // my last column -> right neighbour's left halo column
+        double* q = mc.nb_p[TL_FACE_RIGHT] + (long)mc.nb_off[TL_FACE_RIGHT] + (long)jj * mc.nb_pitch[TL_FACE_RIGHT] +
+                    (g.hd - 1);
+        if (t.kk == last) *q = pv.x;
+        else if (t.kk + 1 == last) *q = pv.y;
+    }
+    if (mc.nb_p[TL_FACE_BOTTOM] && jj == g.hd) { // my first row -> bottom neighbour's top halo row
+        double* q = mc.nb_p[TL_FACE_BOTTOM] + (long)mc.nb_off[TL_FACE_BOTTOM] +
+                    (long)(mc.nb_y[TL_FACE_BOTTOM] - g.hd) * mc.nb_pitch[TL_FACE_BOTTOM] + t.kk;
+        st_pair(q, pv, t.v1);
+    }
+    if (mc.nb_p[TL_FACE_TOP] && jj == g.y - g.hd - 1) { // my last row -> top neighbour's bottom halo row
+        double* q = mc.nb_p[TL_FACE_TOP] + (long)mc.nb_off[TL_FACE_TOP] + (long)(g.hd - 1) * mc.nb_pitch[TL_FACE_TOP] +
+                    t.kk;
+        st_pair(q, pv, t.v1);
+    }
+}
+
 // cg.cpp:257-281 cg_calc_p:  p = beta p + r.  24 B/cell.
 // halo_mask != 0: the CTAs that own chunk-edge cells also write the depth-1 reflective halo of p on
 // the external faces in the mask, so the resident loop needs no separate halo launches.
-template <int U>
+template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal* S, int mode, double beta_imm,
-            int rows, int rev, int halo_mask)
+            int rows, int rev, int halo_mask, double* __restrict__ d_betas, const MultiCtx mc)
 {
+    constexpr bool multi = MULTI;
     double beta = beta_imm;
-    if (mode == SCAL_DEV) {
+    if (mode == SCAL_DEV && !multi) {
         if (!S->p_pending) return;
         beta = S->beta;
     }
     const HotTile t = hot_tile(g, rows, rev);
-    if (!t.v0) return;
-    long i = t.i;
+    if (!MULTI && !t.v0) return;
     const long pitch = g.pitch;
-    const bool edge_tile = halo_mask && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
-                                         blockIdx.x == gridDim.x - 1);
-    for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-        double2 pv[U], rv[U];
+    long i = t.i;
+    double2 pv[U], rv[U];
+    auto load_batch = [&](int jb) {
 #pragma unroll
         for (int q = 0; q < U; ++q) {
             if (jb + q < t.j1) {
@@ -721,18 +892,74 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
                 rv[q] = ld2_ro(r + i + q * pitch);
             }
         }
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (jb + q < t.j1) {
-                pv[q].x = beta * pv[q].x + rv[q].x;
-                pv[q].y = beta * pv[q].y + rv[q].y;
-                st_pair(p + i + q * pitch, pv[q], t.v1);
+    };
+    if constexpr (MULTI) {
+        if (t.v0) load_batch(t.j0); // before the head: overlaps the wait for the peers' r.r partials
+        __shared__ int s_skip;
+        __shared__ double s_beta;
+        if (threadIdx.x == 0) {
+            s_skip = mc_skip(mc, S) ? 1 : 0;
+            if (!s_skip) {
+                const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
+                const double rrn = mc_sum(mc, 1, mc.tl, true, S); // all ranks' r.r, rank order
+                s_beta = rrn / rro;                               // cg_driver.c:106
+                if (blockIdx.x == 0 && blockIdx.y == 0) {         // bookkeeping for the host poll
+                    S->rrn = rrn;
+                    S->beta = s_beta;
+                    d_betas[mc.it_global] = s_beta;               // cg_driver.c:111
+                    S->error = rrn;                               // cg_driver.c:122-123
+                    S->rro = rrn;
+                    S->rro_par[(mc.it_global + 1) & 1] = rrn;     // read by the next iteration's kernels
+                    S->iters = mc.it_global + 1;
+                    if (conv_test(S, rrn) || mc.it_global + 1 >= S->max_iters) {
+                        S->conv = 1;
+                        S->conv_iter = mc.it_global + 1; // this launch (it_global) still completes
+                    }
+                }
             }
         }
-        if (edge_tile) {
+        __syncthreads();
+        if (s_skip) return;
+        beta = s_beta;
+    }
+    if (t.v0) {
+        const bool edge_tile = (halo_mask || multi) && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
+                                                        blockIdx.x == gridDim.x - 1);
+        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+            if (!MULTI || jb != t.j0) load_batch(jb);
 #pragma unroll
-            for (int q = 0; q < U; ++q)
-                if (jb + q < t.j1) p_halo_store(g, p, i + q * pitch, jb + q, pv[q], t, halo_mask);
+            for (int q = 0; q < U; ++q) {
+                if (jb + q < t.j1) {
+                    pv[q].x = beta * pv[q].x + rv[q].x;
+                    pv[q].y = beta * pv[q].y + rv[q].y;
+                    st_pair(p + i + q * pitch, pv[q], t.v1);
+                }
+            }
+            if (edge_tile) {
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+                    if (jb + q < t.j1) {
+                        if (halo_mask) p_halo_store(g, p, i + q * pitch, jb + q, pv[q], t, halo_mask);
+                        if (multi) p_remote_store(g, mc, jb + q, pv[q], t);
+                    }
+            }
+        }
+    }
+    if constexpr (MULTI) {
+        // The last CTA to finish releases the per-face halo flags of the neighbours: every CTA makes its
+        // remote stores visible system-wide before taking its ticket.
+        __shared__ int s_last;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(&S->counter[1], 1u);
+            s_last = (tk == gridDim.x * gridDim.y - 1);
+        }
+        __syncthreads();
+        if (s_last && threadIdx.x < 4) {
+            if (threadIdx.x == 0) S->counter[1] = 0u;
+            if (mc.nb_p[threadIdx.x])
+                st_release_sys(mc.nb_hflag[threadIdx.x], mc.hbase + (unsigned long long)mc.tl + 1ull);
         }
     }
 }
@@ -747,14 +974,20 @@ static int external_mask(const tl_chunk* c)
     return mask;
 }
 
-int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo)
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc)
 {
     const int rows = tile_rows(c, TUNE_P);
     dim3 grid = hot_grid(c, rows);
     const int mask = fuse_halo ? external_mask(c) : 0;
 #define LAUNCH_P(U)                                                                                         \
-    k_cg_calc_p<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal, (int)mode, \
-                                                  beta, rows, rev ? 1 : 0, mask)
+    if (mc && mc->num_ranks > 1)                                                                            \
+        k_cg_calc_p<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal, \
+                                                            (int)mode, beta, rows, rev ? 1 : 0, mask,          \
+                                                            c->d_betas, *mc);                                  \
+    else                                                                                                    \
+        k_cg_calc_p<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R],        \
+                                                             c->scal, (int)mode, beta, rows, rev ? 1 : 0,      \
+                                                             mask, c->d_betas, g_single_ctx)
     switch (g_batch[TUNE_P]) {
     case 1: LAUNCH_P(1); break;
     case 2: LAUNCH_P(2); break;
@@ -878,6 +1111,7 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev)
     TL_TRY(hot_check(c, grid));
     if (!c->p2) {
         TL_CUDA(cudaMalloc((void**)&c->p2, c->field_elems * sizeof(double)));
+        c->p2_alloc = c->p2;
         TL_CUDA(cudaMemsetAsync(c->p2, 0, c->field_elems * sizeof(double), c->stream));
     }
     RedArgs ra{c->partials, c->partial_cap, c->scal};

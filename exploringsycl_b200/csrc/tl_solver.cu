@@ -19,6 +19,9 @@
 #include "tl_internal.h"
 
 int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth);
+unsigned long long tlc_resident_seq_advance(tl_comms* k, int launched);
+
+__global__ void k_set_rro(DevScal* S, double rro) { S->rro = rro; }
 
 static void fields_reset(int* f) { memset(f, 0, sizeof(int) * TL_NUM_EXCHANGE_FIELDS); }
 
@@ -67,6 +70,8 @@ static int cg_init_driver(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, doub
         TL_TRY(tl_fetch_scal(c));
         *rro = c->scal_h->sums[0];
         TL_TRY(sum_ranks(k, rro));
+        k_set_rro<<<1, 1, 0, c->stream>>>(c->scal, *rro); // the resident multi-rank loop starts from it
+        ++g_tl_launches;
     } else {
         TL_TRY(tlk_seed_rro(c)); // rro stays in HBM
     }
@@ -106,7 +111,10 @@ __global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test)
     S->eps = eps;
     S->conv_mode = abs_test;
     S->conv = (S->iters >= stop_iters) ? 1 : 0;
+    S->conv_iter = S->conv ? S->iters : 0x7fffffff;
+    S->rro_par[S->iters & 1] = S->rro;
 }
+
 
 static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_test, int batch, long* launches,
                                bool fused = false)
@@ -174,6 +182,62 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
     return TL_OK;
 }
 
+// Resident CG iterations on N ranks: the same three kernels, but p.w and r.r are combined across
+// ranks inside the kernels (tail CTA -> every rank's slots over NVLink -> head of the next kernel) and
+// calc_p stores its edge cells into the neighbours' halo of p.  No host round trip and no separate
+// halo / all-reduce launches inside the loop; the host only polls the convergence flag per batch.
+static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
+                                     long* launches)
+{
+    k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
+    ++g_tl_launches;
+    if (batch <= 0) batch = 32;
+    DevScal* snaps[2] = {c->scal_h + 1, c->scal_h + 2};
+    cudaEvent_t ev[2] = {c->ev0, c->ev1};
+    const int start = c->resident_iters;
+    int enq = start;
+    MultiCtx mc = c->mc;
+    mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
+    int nb = 0;
+    bool done = (enq >= stop_iters);
+    while (!done) {
+        const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
+        for (int it = 0; it < todo; ++it) {
+            mc.tl = enq + it - start;
+            mc.it_global = enq + it;
+            TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
+            TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc));
+            TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc));
+            *launches += 3;
+        }
+        enq += todo;
+        TL_CUDA(cudaMemcpyAsync(snaps[nb & 1], c->scal, sizeof(DevScal), cudaMemcpyDeviceToHost, c->stream));
+        TL_CUDA(cudaEventRecord(ev[nb & 1], c->stream));
+        if (nb > 0) {
+            TL_CUDA(cudaEventSynchronize(ev[(nb - 1) & 1]));
+            if (snaps[(nb - 1) & 1]->conv) done = true;
+        }
+        ++nb;
+        if (enq >= stop_iters) done = true;
+    }
+    tlc_resident_seq_advance(k, enq - start); // identical on every rank: the poll sees the same flag
+    TL_TRY(tl_fetch_scal(c));
+    c->resident_iters = c->scal_h->iters;
+    if (c->scal_h->pad == 0xdeadu) {
+        tl_set_error("resident CG loop: timed out waiting for a peer rank (site %llu want %llu seen %llu block %llu, "
+                     "iters %d)", c->scal_h->dbg[0], c->scal_h->dbg[1], c->scal_h->dbg[2], c->scal_h->dbg[3],
+                     c->scal_h->iters);
+        return TL_ERR_COMMS;
+    }
+    return TL_OK;
+}
+
+static bool use_resident_multi(const tl_chunk* c, tl_comms* k)
+{
+    const char* e = getenv("TL_MULTI_HOST_DRIVEN");
+    return k && tl_comms_size(k) > 1 && c->has_peers && !(e && e[0] == '1');
+}
+
 static int fetch_cg_coeffs(tl_chunk* c, int n)
 {
     if (n <= 0) return TL_OK;
@@ -203,6 +267,15 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
         tt = converged ? S->iters - 1 : o->max_iters; // loop index printed by cg_driver.c:27
         info->total_iters = S->iters;
         TL_TRY(tl_halo_update(c, k, fields, 1));
+        TL_TRY(fetch_cg_coeffs(c, S->iters));
+    } else if (use_resident_multi(c, k)) {
+        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches));
+        const DevScal* S = c->scal_h;
+        error = S->error;
+        const bool converged = sqrt(fabs(error)) < o->eps;
+        tt = converged ? S->iters - 1 : o->max_iters;
+        info->total_iters = S->iters;
+        TL_TRY(tl_halo_update(c, k, fields, 1)); // u's halo (and p's corners) as after cg_driver.c:22
         TL_TRY(fetch_cg_coeffs(c, S->iters));
     } else {
         for (tt = 0; tt < o->max_iters; ++tt) {
@@ -324,13 +397,18 @@ static int cg_presteps(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, int* fi
     const bool multi = k && tl_comms_size(k) > 1;
     int tt = 0;
     *ended = false;
-    if (!multi) {
+    const bool resident = !multi || use_resident_multi(c, k);
+    auto iterate = [&](int stop, int bt) {
+        return multi ? cg_iterate_resident_multi(c, k, stop, o->eps, 1, bt, launches)
+                     : cg_iterate_resident(c, stop, o->eps, 1, bt, launches);
+    };
+    if (resident) {
         // The rule cannot fire before tt = presteps+1 (or 21 with error_switch): run that many
         // resident iterations (with the |error| < eps end test of cheby_driver.c:70 active on the
         // device), then one at a time while the rule still says "CG".
         int first = o->error_switch ? 21 : o->presteps + 1;
         if (first > o->max_iters) first = o->max_iters;
-        TL_TRY(cg_iterate_resident(c, first, o->eps, 1, o->batch, launches));
+        TL_TRY(iterate(first, o->batch));
         *error = c->scal_h->error;
         if (fabs(*error) < o->eps) {
             *ended = true;
@@ -338,7 +416,7 @@ static int cg_presteps(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, int* fi
         } else {
             tt = c->scal_h->iters;
             while (tt < o->max_iters && !switch_rule(o, 0, tt, *error)) {
-                TL_TRY(cg_iterate_resident(c, tt + 1, o->eps, 1, 1, launches));
+                TL_TRY(iterate(tt + 1, 1));
                 *error = c->scal_h->error;
                 if (fabs(*error) < o->eps) { *ended = true; break; }
                 tt = c->scal_h->iters;

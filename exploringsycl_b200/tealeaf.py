@@ -249,6 +249,12 @@ class Comms:
         check(_lib.lib().tl_comms_send_recv(self.handle, send_buffer, recv_buffer, send_buffer.size, neighbour,
                                             send_tag, recv_tag))
 
+    def post(self, send_buffer, neighbour, send_tag):  # the MPI_Isend half
+        check(_lib.lib().tl_comms_post(self.handle, send_buffer, send_buffer.size, neighbour, send_tag))
+
+    def recv(self, recv_buffer, neighbour, recv_tag):  # the MPI_Irecv + wait half
+        check(_lib.lib().tl_comms_recv(self.handle, recv_buffer, recv_buffer.size, neighbour, recv_tag))
+
     def finalise(self):
         if self.handle:
             _lib.lib().tl_comms_destroy(self.handle)

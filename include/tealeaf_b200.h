@@ -169,6 +169,10 @@ int tl_comms_min(tl_comms* k, double* a);              /* min_over_ranks,   comm
  * `neighbour` under send_tag and receives the neighbour's message posted under recv_tag. */
 int tl_comms_send_recv(tl_comms* k, const double* send_buffer, double* recv_buffer, int buffer_len,
                        int neighbour, int send_tag, int recv_tag);
+/* The two halves separately (MPI_Isend / MPI_Irecv+MPI_Wait): post every message of a phase, then
+ * receive them, as wait_for_requests does after remote_halo_driver.c:32-55 posted them. */
+int tl_comms_post(tl_comms* k, const double* send_buffer, int buffer_len, int neighbour, int send_tag);
+int tl_comms_recv(tl_comms* k, double* recv_buffer, int buffer_len, int neighbour, int recv_tag);
 /* Attach a chunk: exchanges CUDA-IPC handles of its face staging buffers / scalar slots with the
  * neighbouring ranks so that halo_update and the solver loops move data peer to peer. */
 int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c);
