@@ -50,6 +50,7 @@ struct ShmHeader {
     unsigned long long arena_face_elems[TLC_MAX_RANKS];
     int arena_device[TLC_MAX_RANKS];
     int geo[TLC_MAX_RANKS][4];                // x, y, pitch, off of each rank's chunk
+    unsigned long long field_elems[TLC_MAX_RANKS]; // doubles per field inside each rank's slab
 };
 
 struct tl_comms {
@@ -384,6 +385,7 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
     h->geo[k->rank][1] = c->g.y;
     h->geo[k->rank][2] = c->g.pitch;
     h->geo[k->rank][3] = c->g.off;
+    h->field_elems[k->rank] = c->field_elems;
     TL_TRY(tl_comms_barrier(k));
     size_t fe = 0;
     for (int r = 0; r < k->num_ranks; ++r) fe = h->arena_face_elems[r] > fe ? h->arena_face_elems[r] : fe;
@@ -399,7 +401,7 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
         TL_TRY(block_offset(k->arena, &o1));
         TL_TRY(block_offset(c->slab, &o2));
         h->arena_off[k->rank] = o1;
-        h->pfield_off[k->rank] = o2 + (unsigned long long)((char*)(c->slab + (size_t)TL_FIELD_P * c->field_elems) - (char*)c->slab);
+        h->pfield_off[k->rank] = o2; // offset of the slab inside its allocation block
     }
     std::atomic_thread_fence(std::memory_order_release);
     TL_TRY(tl_comms_barrier(k));
@@ -449,7 +451,8 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
         double* base = (double*)k->peer_arena[n];
         c->nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
         c->nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
-        mc.nb_p[f] = (double*)k->peer_pfield[n];
+        mc.nb_p[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_P * h->field_elems[n];
+        mc.nb_r[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_R * h->field_elems[n];
         mc.nb_hflag[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_HFLAGS) + opposite[f];
         mc.nb_x[f] = h->geo[n][0];
         mc.nb_y[f] = h->geo[n][1];

@@ -64,6 +64,7 @@ struct MultiCtx {
     double* slots_peer[TL_MAX_PEERS];
     unsigned long long* sflags_peer[TL_MAX_PEERS];
     double* nb_p[4];              // neighbour's p field base (peer-mapped), by my face; null if external
+    double* nb_r[4];              // neighbour's r field base (fused loop: r's halo is what travels)
     unsigned long long* nb_hflag[4]; // neighbour's halo flag of the opposite face
     int nb_pitch[4], nb_x[4], nb_y[4], nb_off[4];
 };
@@ -146,9 +147,9 @@ int tlk_local_halos(tl_chunk* c, const int fields[6], int depth);
 int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len);
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr);                // -> scal->pw (& alpha when SCAL_DEV)
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr); // -> scal->rrn (& beta, conv when SCAL_DEV)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false); // -> scal->rrn (& beta, conv when SCAL_DEV)
 int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc = nullptr);
-int tlk_cg_calc_pw(tl_chunk* c, bool rev);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
+int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc = nullptr);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
 int tlk_cheby_calc_u(tl_chunk* c);

@@ -40,8 +40,8 @@ struct RedArgs {
 };
 
 // Deterministic single-pass grid reduction.  Every CTA writes its NR tile partials; the CTA that
-// takes the last ticket sums all tile partials in a fixed order.  Returns true in thread 0 of
-// that last CTA with the totals in `tot`.
+// takes the last ticket sums all tile partials in a fixed order.  Returns true in EVERY thread of
+// that last CTA with the totals in `tot` (callers do their scalar bookkeeping in thread 0).
 template <int NR>
 __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
                                             double (&tot)[NR])
@@ -79,13 +79,10 @@ __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra
         if (lane == 0) sm[r][wid] = s;
     }
     __syncthreads();
-    if (tid == 0) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) tot[r] = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
-        ra.S->counter[0] = 0u;
-        return true;
-    }
-    return false;
+    for (int r = 0; r < NR; ++r) tot[r] = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
+    if (tid == 0) ra.S->counter[0] = 0u;
+    return true;
 }
 
 // shared.h:59-63 -- the reference SMVP association, spelled out on registers:
@@ -118,7 +115,8 @@ __global__ void __launch_bounds__(TL_TPB) k_generic(Geo g, int k_lo, int k_hi, i
     if constexpr (NR > 0) {
         double tot[NR > 0 ? NR : 1];
         const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        if (grid_reduce<(NR > 0 ? NR : 1)>(acc, ra, tile, gridDim.x * gridDim.y, tot)) fin(tot, ra.S);
+        if (grid_reduce<(NR > 0 ? NR : 1)>(acc, ra, tile, gridDim.x * gridDim.y, tot) && threadIdx.x == 0)
+            fin(tot, ra.S);
     }
 }
 
@@ -454,7 +452,7 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p)
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// Spin until *flag >= want.  Bounded (~20 s) so that a lost peer cannot hang the GPU: on timeout an
+// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU: on timeout an
 // error mark is left in DevScal.pad and the caller carries on with whatever is there.
 __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
                                           unsigned long long site = 0)
@@ -463,7 +461,7 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
     unsigned long long seen;
     while ((seen = ld_acquire_sys(flag)) < want) {
         if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
-        if (clock64() - t0 > 4000000000LL) { // ~2 s
+        if (clock64() - t0 > 20000000000LL) { // ~10 s
             if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
                 S->dbg[0] = site;
                 S->dbg[1] = want;
@@ -475,29 +473,34 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
         __nanosleep(64);
     }
 }
-// Sum of the N ranks' partials of (kind, local iteration tl) in rank order; waits for their flags
-// when `wait` (the partials of an earlier iteration are already complete).
-__device__ __forceinline__ double mc_sum(const MultiCtx& mc, int kind, int tl, bool wait, DevScal* S)
+// Sum of the N ranks' partials of (kind, local iteration tl) in rank order.  Called by ALL 32 lanes of
+// warp 0: lane r waits for rank r's flag and loads its partial (the N memory latencies overlap), then
+// the partials are added in rank order, identically on every rank (same order as tl_comms_sum).
+__device__ __forceinline__ double mc_sum_warp(const MultiCtx& mc, int kind, int tl, DevScal* S)
 {
-    const int par = tl & 1;
-    double s = 0.0;
-    for (int r = 0; r < mc.num_ranks; ++r) {
-        const int idx = TL_SLOT_IDX(kind, par, r);
-        if (wait) spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
-                            1000ull + 100ull * kind + 10ull * r + (unsigned long long)tl * 100000ull);
-        const double v = ld_volatile_f64(mc.slots_local + idx);
-        s = (r == 0) ? v : s + v;
+    const int lane = threadIdx.x & 31;
+    double v = 0.0;
+    if (lane < mc.num_ranks) {
+        const int idx = TL_SLOT_IDX(kind, tl & 1, lane);
+        spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
+                  1000ull + 100ull * kind + 10ull * lane + (unsigned long long)tl * 100000ull);
+        v = ld_volatile_f64(mc.slots_local + idx);
     }
+    double s = __shfl_sync(0xffffffffu, v, 0);
+    for (int r = 1; r < mc.num_ranks; ++r) s = s + __shfl_sync(0xffffffffu, v, r);
     return s;
 }
-// Tail of a reduction kernel: this rank's partial goes to every rank's slot, then the flag.
-__device__ __forceinline__ void mc_publish(const MultiCtx& mc, int kind, double partial)
+// Tail of a reduction kernel, called by all lanes of warp 0 of the last CTA: lane r stores this rank's
+// partial into rank r's slot, fences, then releases rank r's flag.
+__device__ __forceinline__ void mc_publish_warp(const MultiCtx& mc, int kind, double partial)
 {
-    const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
-    for (int r = 0; r < mc.num_ranks; ++r) mc.slots_peer[r][idx] = partial;
-    __threadfence_system();
-    for (int r = 0; r < mc.num_ranks; ++r)
-        st_release_sys(mc.sflags_peer[r] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
+    const int lane = threadIdx.x & 31;
+    if (lane < mc.num_ranks) {
+        const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
+        mc.slots_peer[lane][idx] = partial;
+        __threadfence_system();
+        st_release_sys(mc.sflags_peer[lane] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
+    }
 }
 __device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
 {
@@ -533,6 +536,34 @@ __device__ __forceinline__ HotTile hot_tile(const Geo& g, int rows, int rev)
     t.tile = by * gridDim.x + bx;
     t.ntiles = gridDim.x * gridDim.y;
     return t;
+}
+
+// Multi-rank: the thread that owns an edge cell of an INTERNAL face stores the updated p straight into
+// the neighbour's halo cell over NVLink (what pack -> MPI -> unpack does in remote_halo_driver.c for
+// depth 1; the 5-point stencil never reads halo corners, so none are sent).
+__device__ __forceinline__ void edge_remote_store(const Geo& g, const MultiCtx& mc, double* const* nbf, int jj,
+                                                  double2 pv, const HotTile& t)
+{
+    const int last = g.x - g.hd - 1;
+    if (nbf[TL_FACE_LEFT] && t.kk == g.hd) // my first column -> left neighbour's right halo column
+        nbf[TL_FACE_LEFT][(long)mc.nb_off[TL_FACE_LEFT] + (long)jj * mc.nb_pitch[TL_FACE_LEFT] +
+                              (mc.nb_x[TL_FACE_LEFT] - g.hd)] = pv.x;
+    if (nbf[TL_FACE_RIGHT]) { // my last column -> right neighbour's left halo column
+        double* q = nbf[TL_FACE_RIGHT] + (long)mc.nb_off[TL_FACE_RIGHT] + (long)jj * mc.nb_pitch[TL_FACE_RIGHT] +
+                    (g.hd - 1);
+        if (t.kk == last) *q = pv.x;
+        else if (t.kk + 1 == last) *q = pv.y;
+    }
+    if (nbf[TL_FACE_BOTTOM] && jj == g.hd) { // my first row -> bottom neighbour's top halo row
+        double* q = nbf[TL_FACE_BOTTOM] + (long)mc.nb_off[TL_FACE_BOTTOM] +
+                    (long)(mc.nb_y[TL_FACE_BOTTOM] - g.hd) * mc.nb_pitch[TL_FACE_BOTTOM] + t.kk;
+        st_pair(q, pv, t.v1);
+    }
+    if (nbf[TL_FACE_TOP] && jj == g.y - g.hd - 1) { // my last row -> top neighbour's bottom halo row
+        double* q = nbf[TL_FACE_TOP] + (long)mc.nb_off[TL_FACE_TOP] + (long)(g.hd - 1) * mc.nb_pitch[TL_FACE_TOP] +
+                    t.kk;
+        st_pair(q, pv, t.v1);
+    }
 }
 
 // Tuning knobs (tl_set_tuning): rows per tile and rows per load batch for each hot kernel family.
@@ -651,13 +682,16 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
     }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
-        S->pw = tot[0];
         if (multi) {
-            mc_publish(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
-        } else if (mode == SCAL_DEV) {
-            const double alpha = S->rro / tot[0]; // cg_driver.c:87
-            S->alpha = alpha;
-            d_alphas[S->iters] = alpha;           // cg_driver.c:93
+            if (threadIdx.x < 32) mc_publish_warp(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
+        }
+        if (threadIdx.x == 0) {
+            S->pw = tot[0];
+            if (!multi && mode == SCAL_DEV) {
+                const double alpha = S->rro / tot[0]; // cg_driver.c:87
+                S->alpha = alpha;
+                d_alphas[S->iters] = alpha;           // cg_driver.c:93
+            }
         }
     }
 }
@@ -696,7 +730,7 @@ template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double* __restrict__ p,
              const double* __restrict__ w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
-             int rows, int rev, double* __restrict__ d_alphas, const MultiCtx mc)
+             int rows, int rev, double* __restrict__ d_alphas, const MultiCtx mc, int send_r_halo)
 {
     DevScal* S = ra.S;
     constexpr bool multi = MULTI;
@@ -728,18 +762,21 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
         if (t.v0) load_batch(t.j0);
         __shared__ int s_skip;
         __shared__ double s_alpha;
-        if (threadIdx.x == 0) {
-            s_skip = mc_skip(mc, S) ? 1 : 0;
-            if (!s_skip) {
+        if (threadIdx.x < 32) {
+            const bool skip = mc_skip(mc, S);
+            if (!skip) {
                 const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
-                const double pw = mc_sum(mc, 0, mc.tl, true, S); // all ranks' p.w, rank order
-                s_alpha = rro / pw;                               // cg_driver.c:87
-                if (blockIdx.x == 0 && blockIdx.y == 0) {
-                    S->pw = pw;
-                    S->alpha = s_alpha;
-                    d_alphas[mc.it_global] = s_alpha;             // cg_driver.c:93
+                const double pw = mc_sum_warp(mc, 0, mc.tl, S);   // all ranks' p.w, rank order
+                if (threadIdx.x == 0) {
+                    s_alpha = rro / pw;                           // cg_driver.c:87
+                    if (blockIdx.x == 0 && blockIdx.y == 0) {
+                        S->pw = pw;
+                        S->alpha = s_alpha;
+                        d_alphas[mc.it_global] = s_alpha;         // cg_driver.c:93
+                    }
                 }
             }
+            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
         }
         __syncthreads();
         if (s_skip) return;
@@ -760,15 +797,30 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
                     st_pair(r + iq, rv[q], t.v1);
                     acc[0] += rv[q].x * rv[q].x;
                     if (t.v1) acc[0] += rv[q].y * rv[q].y;
+                    if constexpr (MULTI) { // fused loop: the updated r edge cells go to the neighbours' halo of r
+                        if (send_r_halo) edge_remote_store(g, mc, mc.nb_r, jb + q, rv[q], t);
+                    }
                 }
             }
         }
     }
+    if constexpr (MULTI) {
+        // only the edge tiles made remote halo stores: they must be visible system-wide before this CTA's ticket
+        const bool edge_tile = (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+        if (send_r_halo && edge_tile) __threadfence_system();
+    }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        if (multi) {
+            if (threadIdx.x < 32) mc_publish_warp(mc, 1, tot[0]); // sum_over_ranks(rrn), cg_driver.c:104, over NVLink
+            if (send_r_halo && threadIdx.x >= 32 && threadIdx.x < 36) { // every CTA fenced its halo stores before its ticket
+                const int f = threadIdx.x - 32;
+                if (mc.nb_r[f]) st_release_sys(mc.nb_hflag[f], mc.hbase + (unsigned long long)mc.tl + 1ull);
+            }
+        }
+        if (threadIdx.x != 0) return;
         S->rrn = tot[0];
         if (multi) {
-            mc_publish(mc, 1, tot[0]); // sum_over_ranks(rrn), cg_driver.c:104, over NVLink
         } else if (mode == SCAL_DEV) {
             const double rrn = tot[0];
             const double beta = rrn / S->rro; // cg_driver.c:106
@@ -784,7 +836,7 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
     }
 }
 
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc, bool send_r_halo)
 {
     const int rows = tile_rows(c, TUNE_UR);
     dim3 grid = hot_grid(c, rows);
@@ -795,12 +847,12 @@ int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const Mul
         k_cg_calc_ur<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],        \
                                                              c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra, \
                                                              (int)mode, alpha, rows, rev ? 1 : 0, c->d_alphas, \
-                                                             *mc);                                             \
+                                                             *mc, send_r_halo ? 1 : 0);                        \
     else                                                                                                   \
         k_cg_calc_ur<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],       \
                                                               c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas,  \
                                                               ra, (int)mode, alpha, rows, rev ? 1 : 0,          \
-                                                              c->d_alphas, g_single_ctx)
+                                                              c->d_alphas, g_single_ctx, 0)
     switch (g_batch[TUNE_UR]) {
     case 1: LAUNCH_UR(1); break;
     case 2: LAUNCH_UR(2); break;
@@ -838,33 +890,6 @@ __device__ __forceinline__ void p_halo_store(const Geo& g, double* p, long i, in
     }
 }
 
-// Multi-rank: the thread that owns an edge cell of an INTERNAL face stores the updated p straight into
-// the neighbour's halo cell over NVLink (what pack -> MPI -> unpack does in remote_halo_driver.c for
-// depth 1; the 5-point stencil never reads halo corners, so none are sent).
-__device__ __forceinline__ void p_remote_store(const Geo& g, const MultiCtx& mc, int jj, double2 pv, const HotTile& t)
-{
-    const int last = g.x - g.hd - 1;
-    if (mc.nb_p[TL_FACE_LEFT] && t.kk == g.hd) // my first column -> left neighbour's right halo column
-        mc.nb_p[TL_FACE_LEFT][(long)mc.nb_off[TL_FACE_LEFT] + (long)jj * mc.nb_pitch[TL_FACE_LEFT] +
-                              (mc.nb_x[TL_FACE_LEFT] - g.hd)] = pv.x;
-    if (mc.nb_p[TL_FACE_RIGHT]) { // my last column -> right neighbour's left halo column
-        double* q = mc.nb_p[TL_FACE_RIGHT] + (long)mc.nb_off[TL_FACE_RIGHT] + (long)jj * mc.nb_pitch[TL_FACE_RIGHT] +
-                    (g.hd - 1);
-        if (t.kk == last) *q = pv.x;
-        else if (t.kk + 1 == last) *q = pv.y;
-    }
-    if (mc.nb_p[TL_FACE_BOTTOM] && jj == g.hd) { // my first row -> bottom neighbour's top halo row
-        double* q = mc.nb_p[TL_FACE_BOTTOM] + (long)mc.nb_off[TL_FACE_BOTTOM] +
-                    (long)(mc.nb_y[TL_FACE_BOTTOM] - g.hd) * mc.nb_pitch[TL_FACE_BOTTOM] + t.kk;
-        st_pair(q, pv, t.v1);
-    }
-    if (mc.nb_p[TL_FACE_TOP] && jj == g.y - g.hd - 1) { // my last row -> top neighbour's bottom halo row
-        double* q = mc.nb_p[TL_FACE_TOP] + (long)mc.nb_off[TL_FACE_TOP] + (long)(g.hd - 1) * mc.nb_pitch[TL_FACE_TOP] +
-                    t.kk;
-        st_pair(q, pv, t.v1);
-    }
-}
-
 // cg.cpp:257-281 cg_calc_p:  p = beta p + r.  24 B/cell.
 // halo_mask != 0: the CTAs that own chunk-edge cells also write the depth-1 reflective halo of p on
 // the external faces in the mask, so the resident loop needs no separate halo launches.
@@ -897,16 +922,17 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
         if (t.v0) load_batch(t.j0); // before the head: overlaps the wait for the peers' r.r partials
         __shared__ int s_skip;
         __shared__ double s_beta;
-        if (threadIdx.x == 0) {
-            s_skip = mc_skip(mc, S) ? 1 : 0;
-            if (!s_skip) {
+        if (threadIdx.x < 32) {
+            const bool skip = mc_skip(mc, S);
+            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
+            if (!skip) {
                 const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
-                const double rrn = mc_sum(mc, 1, mc.tl, true, S); // all ranks' r.r, rank order
-                s_beta = rrn / rro;                               // cg_driver.c:106
-                if (blockIdx.x == 0 && blockIdx.y == 0) {         // bookkeeping for the host poll
+                const double rrn = mc_sum_warp(mc, 1, mc.tl, S);  // all ranks' r.r, rank order
+                if (threadIdx.x == 0) s_beta = rrn / rro;         // cg_driver.c:106
+                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { // bookkeeping for the host poll
                     S->rrn = rrn;
-                    S->beta = s_beta;
-                    d_betas[mc.it_global] = s_beta;               // cg_driver.c:111
+                    S->beta = rrn / rro;
+                    d_betas[mc.it_global] = rrn / rro;            // cg_driver.c:111
                     S->error = rrn;                               // cg_driver.c:122-123
                     S->rro = rrn;
                     S->rro_par[(mc.it_global + 1) & 1] = rrn;     // read by the next iteration's kernels
@@ -940,7 +966,7 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
                 for (int q = 0; q < U; ++q)
                     if (jb + q < t.j1) {
                         if (halo_mask) p_halo_store(g, p, i + q * pitch, jb + q, pv[q], t, halo_mask);
-                        if (multi) p_remote_store(g, mc, jb + q, pv[q], t);
+                        if (multi) edge_remote_store(g, mc, mc.nb_p, jb + q, pv[q], t);
                     }
             }
         }
@@ -949,7 +975,8 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
         // The last CTA to finish releases the per-face halo flags of the neighbours: every CTA makes its
         // remote stores visible system-wide before taking its ticket.
         __shared__ int s_last;
-        __threadfence_system();
+        const bool edge_cta = (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
+        if (edge_cta) __threadfence_system(); // only edge tiles made remote stores
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int tk = atomicAdd(&S->counter[1], 1u);
@@ -1009,15 +1036,61 @@ int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_h
 // there; on internal faces the halo of p (old) and r must have been exchanged.
 // Old p is read by neighbouring tiles while this tile overwrites it, so the update is double
 // buffered: reads come from p_in, writes go to p_out (the chunk's P and P2 buffers swap roles).
-template <int U>
+template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out, const double* __restrict__ r,
              const double* __restrict__ kx, const double* __restrict__ ky, double* __restrict__ w,
-             double* __restrict__ d_alphas, RedArgs ra, int rows, int rev, int ext_mask)
+             double* __restrict__ d_alphas, double* __restrict__ d_betas, RedArgs ra, int rows, int rev, int ext_mask,
+             const MultiCtx mc)
 {
     DevScal* S = ra.S;
-    if (S->conv) return;
-    const double beta = S->beta;
+    double beta;
+    if constexpr (!MULTI) {
+        if (S->conv) return;
+        beta = S->beta;
+    } else {
+        // Multi-rank head: beta_{t-1} = rrn_{t-1} / rro_{t-1} from all ranks' r.r partials (rank order);
+        // every CTA takes the same convergence decision from the same sum.  The tiles are tall (one wave),
+        // so this runs once per CTA at kernel start.  Edge tiles then wait for the neighbours' r halo.
+        __shared__ int s_skip;
+        __shared__ double s_beta;
+        if (threadIdx.x < 32) {
+            bool skip = mc_skip(mc, S);
+            if (!skip) {
+                const double rro_prev = *(volatile double*)&S->rro_par[(mc.it_global - 1) & 1];
+                const double rrn = mc_sum_warp(mc, 1, mc.tl - 1, S);
+                const bool conv = conv_test(S, rrn);                  // cg_driver.c:24
+                if (threadIdx.x == 0) s_beta = rrn / rro_prev;        // cg_driver.c:106
+                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { // bookkeeping of iteration t-1
+                    S->rrn = rrn;
+                    S->beta = rrn / rro_prev;
+                    d_betas[mc.it_global - 1] = rrn / rro_prev;       // cg_driver.c:111
+                    S->error = rrn;
+                    S->rro = rrn;
+                    S->rro_par[mc.it_global & 1] = rrn;               // cg_driver.c:123
+                    S->iters = mc.it_global;
+                    if (conv) {
+                        S->conv = 1;
+                        S->conv_iter = mc.it_global;
+                    }
+                }
+                if (conv) skip = true;
+                if (!skip && threadIdx.x == 0) {
+                    const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+                    const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+                    const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
+                    if (bx == 0 && mc.nb_r[TL_FACE_LEFT]) spin_flag(mc.hflags_local + TL_FACE_LEFT, want, S, 11ull);
+                    if (bx == gridDim.x - 1 && mc.nb_r[TL_FACE_RIGHT]) spin_flag(mc.hflags_local + TL_FACE_RIGHT, want, S, 12ull);
+                    if (by == 0 && mc.nb_r[TL_FACE_BOTTOM]) spin_flag(mc.hflags_local + TL_FACE_BOTTOM, want, S, 13ull);
+                    if (by == gridDim.y - 1 && mc.nb_r[TL_FACE_TOP]) spin_flag(mc.hflags_local + TL_FACE_TOP, want, S, 14ull);
+                }
+            }
+            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_skip) return;
+        beta = s_beta;
+    }
     const HotTile t = hot_tile(g, rows, rev);
     const long pitch = g.pitch;
     const int lane = threadIdx.x & 31;
@@ -1029,6 +1102,10 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
     const bool load_l = t.v0 && !mir_l && lane == 0;
     // the right neighbour of cell 1 lives in lane+1 unless I am lane 31 or that lane is past the row end
     const bool load_r = t.v1 && !mir_r1 && (lane == 31 || t.kk + 2 > khi);
+    // internal faces (multi-rank): the ring values I compute for the halo cells are also the next
+    // iteration's old p there, so they are written to p_out's halo
+    const bool halo_l = MULTI && t.v0 && !(ext_mask & 1) && t.kk == klo;
+    const bool halo_r = MULTI && !(ext_mask & 2) && ((t.v1 && t.kk + 1 == khi) || (t.v0 && !t.v1 && t.kk == khi));
     auto pnew2 = [&](long i) {
         double2 a = ld2_ro(p_in + i);
         const double2 b = ld2_ro(r + i);
@@ -1054,6 +1131,7 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
         pc = pnew2(i);
         const bool mir_b = (ext_mask & 4) && t.j0 == jlo;
         pm = mir_b ? pc : pnew2(i - pitch);
+        if (MULTI && !(ext_mask & 4) && t.j0 == jlo) st_pair(p_out + i - pitch, pm, t.v1); // bottom halo row
         kyc = ld2_ro(ky + i);
     }
     sides(pc, i, pl, pr);
@@ -1082,10 +1160,19 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
                 sides(pn[u], iu + pitch, pln, prn);
                 if (t.v0) {
                     double2 wv;
-                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, mir_r0 ? pc.x : pc.y, pm.x, pn[u].x);
+                    const double pr0 = mir_r0 ? pc.x : pc.y; // right neighbour of cell 0
+                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pr0, pm.x, pn[u].x);
                     wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
                     st_pair(w + iu, wv, t.v1);
                     st_pair(p_out + iu, pc, t.v1);
+                    if constexpr (MULTI) {
+                        if (halo_l) p_out[iu - 1] = pl;
+                        if (halo_r) {
+                            if (t.v1) p_out[iu + 2] = pr;
+                            else p_out[iu + 1] = pc.y;
+                        }
+                        if (!(ext_mask & 8) && jb + u == jhi) st_pair(p_out + iu + pitch, pn[u], t.v1); // top halo row
+                    }
                     acc[0] += wv.x * pc.x;
                     if (t.v1) acc[0] += wv.y * pc.y;
                     pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln; pr = prn;
@@ -1095,16 +1182,22 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
     }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        if constexpr (MULTI) {
+            if (threadIdx.x < 32) mc_publish_warp(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
+        }
+        if (threadIdx.x != 0) return;
         S->pw = tot[0];
-        const double alpha = S->rro / tot[0];
-        S->alpha = alpha;
-        d_alphas[S->iters] = alpha;
-        S->p_pending = 0; // the pending p update of the previous iteration has now been applied
+        if constexpr (!MULTI) {
+            const double alpha = S->rro / tot[0];
+            S->alpha = alpha;
+            d_alphas[S->iters] = alpha;
+            S->p_pending = 0; // the pending p update of the previous iteration has now been applied
+        }
     }
 }
 
 // p_in = c->f[P], p_out = c->p2; the caller swaps them after the launch.
-int tlk_cg_calc_pw(tl_chunk* c, bool rev)
+int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc)
 {
     const int rows = tile_rows(c, TUNE_PW);
     dim3 grid = hot_grid(c, rows);
@@ -1117,9 +1210,16 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev)
     RedArgs ra{c->partials, c->partial_cap, c->scal};
     const int mask = external_mask(c);
 #define LAUNCH_PW(U)                                                                                          \
-    k_cg_calc_pw<U><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],             \
-                                                   c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W],       \
-                                                   c->d_alphas, ra, rows, rev ? 1 : 0, mask)
+    if (mc && mc->num_ranks > 1)                                                                              \
+        k_cg_calc_pw<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],    \
+                                                             c->f[TL_FIELD_KX], c->f[TL_FIELD_KY],               \
+                                                             c->f[TL_FIELD_W], c->d_alphas, c->d_betas, ra, rows, \
+                                                             rev ? 1 : 0, mask, *mc);                            \
+    else                                                                                                      \
+        k_cg_calc_pw<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],   \
+                                                              c->f[TL_FIELD_KX], c->f[TL_FIELD_KY],              \
+                                                              c->f[TL_FIELD_W], c->d_alphas, c->d_betas, ra,     \
+                                                              rows, rev ? 1 : 0, mask, g_single_ctx)
     switch (g_batch[TUNE_PW]) {
     case 1: LAUNCH_PW(1); break;
     case 2: LAUNCH_PW(2); break;

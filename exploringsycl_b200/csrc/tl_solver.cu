@@ -22,6 +22,7 @@ int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth);
 unsigned long long tlc_resident_seq_advance(tl_comms* k, int launched);
 
 __global__ void k_set_rro(DevScal* S, double rro) { S->rro = rro; }
+__global__ void k_clear_conv_stamp(DevScal* S) { S->conv_iter = 0x7fffffff; }
 
 static void fields_reset(int* f) { memset(f, 0, sizeof(int) * TL_NUM_EXCHANGE_FIELDS); }
 
@@ -187,7 +188,7 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
 // calc_p stores its edge cells into the neighbours' halo of p.  No host round trip and no separate
 // halo / all-reduce launches inside the loop; the host only polls the convergence flag per batch.
 static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
-                                     long* launches)
+                                     long* launches, bool fused = false)
 {
     k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
     ++g_tl_launches;
@@ -195,20 +196,33 @@ static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, d
     DevScal* snaps[2] = {c->scal_h + 1, c->scal_h + 2};
     cudaEvent_t ev[2] = {c->ev0, c->ev1};
     const int start = c->resident_iters;
+    if (fused && start != 0) fused = false; // the fused kernel needs the previous iteration's r.r slots
     int enq = start;
     MultiCtx mc = c->mc;
     mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
-    int nb = 0;
+    int nb = 0, n_pw = 0;
     bool done = (enq >= stop_iters);
     while (!done) {
         const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
         for (int it = 0; it < todo; ++it) {
             mc.tl = enq + it - start;
             mc.it_global = enq + it;
-            TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
-            TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc));
-            TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc));
-            *launches += 3;
+            if (!fused) {
+                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc));
+                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc));
+                *launches += 3;
+            } else {
+                // two kernels per iteration: r's halo (not p's) travels, the ring of updated p is recomputed
+                if (mc.tl == 0) {
+                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
+                } else {
+                    TL_TRY(tlk_cg_calc_pw(c, false, &mc));
+                    ++n_pw;
+                }
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, true));
+                *launches += 2;
+            }
         }
         enq += todo;
         TL_CUDA(cudaMemcpyAsync(snaps[nb & 1], c->scal, sizeof(DevScal), cudaMemcpyDeviceToHost, c->stream));
@@ -222,6 +236,36 @@ static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, d
     }
     tlc_resident_seq_advance(k, enq - start); // identical on every rank: the poll sees the same flag
     TL_TRY(tl_fetch_scal(c));
+    if (fused) {
+        // iterations actually executed: up to the convergence stamp, else everything that was launched
+        const int executed = c->scal_h->conv ? c->scal_h->conv_iter : enq;
+        const int executed_pw = executed > 0 ? executed - 1 : 0;
+        if ((n_pw - executed_pw) & 1) { // undo the host-side P/P2 swaps of launches that were no-ops
+            double* tmp = c->f[TL_FIELD_P];
+            c->f[TL_FIELD_P] = c->p2;
+            c->p2 = tmp;
+        }
+        if (executed > 0) {
+            // the last iteration's p update (and its bookkeeping: beta, error, iteration count) is pending
+            MultiCtx fin = mc;
+            fin.tl = executed - 1 - start;
+            fin.it_global = executed - 1;
+            for (int f = 0; f < 4; ++f) fin.nb_p[f] = nullptr; // halos are refreshed by the generic exchange below
+            k_clear_conv_stamp<<<1, 1, 0, c->stream>>>(c->scal);
+            ++g_tl_launches;
+            TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &fin));
+            *launches += 1;
+            TL_TRY(tl_fetch_scal(c));
+        }
+        // Neighbours address this chunk's p through the slab mapping (three-kernel loop): leave p there.
+        double* slab_p = c->slab + (size_t)TL_FIELD_P * c->field_elems;
+        if (c->f[TL_FIELD_P] != slab_p) {
+            TL_CUDA(cudaMemcpyAsync(slab_p, c->f[TL_FIELD_P], c->field_elems * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+            c->p2 = c->f[TL_FIELD_P];
+            c->f[TL_FIELD_P] = slab_p;
+        }
+    }
     c->resident_iters = c->scal_h->iters;
     if (c->scal_h->pad == 0xdeadu) {
         tl_set_error("resident CG loop: timed out waiting for a peer rank (site %llu want %llu seen %llu block %llu, "
@@ -269,7 +313,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
         TL_TRY(tl_halo_update(c, k, fields, 1));
         TL_TRY(fetch_cg_coeffs(c, S->iters));
     } else if (use_resident_multi(c, k)) {
-        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches));
+        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w == 2));
         const DevScal* S = c->scal_h;
         error = S->error;
         const bool converged = sqrt(fabs(error)) < o->eps;

@@ -196,7 +196,9 @@ typedef struct {
     int error_switch;      /* settings.h:32 */
     double eps_lim;        /* settings.h:34 */
     int check_result;      /* settings.h:35: residual + 2norm in solve_finished */
-    int fuse_p_into_w;     /* 0: three kernels per CG iteration as in cg_driver.c; 1: p-update fused into the next matvec */
+    int fuse_p_into_w;     /* 0: three kernels per CG iteration as in cg_driver.c; 1 (default): p-update fused into the
+                            * next matvec on one rank, three kernels on several ranks (measured faster there);
+                            * 2: fused on several ranks too (r's halo travels instead of p's). Same results. */
     int batch;             /* iterations enqueued between convergence polls (0 = default) */
 } tl_solve_opts;
 
