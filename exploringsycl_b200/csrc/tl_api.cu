@@ -118,6 +118,8 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     cudaStreamSynchronize(c->stream);
     cudaFree(c->slab);
     if (c->p2_alloc) cudaFree(c->p2_alloc);
+    for (int f = 0; f < TL_NUM_FIELDS; ++f)
+        if (c->alt_alloc[f]) cudaFree(c->alt_alloc[f]);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->scal); cudaFreeHost(c->scal_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas); cudaFree(c->d_cheby);

@@ -83,6 +83,8 @@ struct tl_chunk {
     double *cell_x, *cell_y, *vertex_x, *vertex_y; // device 1-D
     double* p2;                   // device, second p buffer of the fused p+w kernel (lazily allocated)
     double* p2_alloc;             // the allocation behind it (P and P2 swap roles; this is what gets freed)
+    double* alt[TL_NUM_FIELDS];   // second buffers of the fused Chebyshev (U) / PPCG (SD) kernels, lazily allocated
+    double* alt_alloc[TL_NUM_FIELDS];
     double* partials;             // device, per-tile partial sums (4 lanes)
     int partial_cap;              // tiles
     DevScal* scal;                // device
@@ -153,6 +155,9 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc = nullptr);        
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
 int tlk_cheby_calc_u(tl_chunk* c);
+int tlk_cheby_fused(tl_chunk* c, double alpha, double beta);  // cheby_iterate + cheby_calc_u in one pass; swaps U buffers
+int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta);   // ppcg_calc_ur + ppcg_calc_sd in one pass; swaps SD buffers
+int tlk_field_home(tl_chunk* c, int field);                   // move a double-buffered field back into the slab
 int tlk_ppcg_init(tl_chunk* c, double theta);
 int tlk_ppcg_calc_ur(tl_chunk* c);
 int tlk_ppcg_calc_sd(tl_chunk* c, double alpha, double beta);

@@ -1235,6 +1235,145 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused Chebyshev / PPCG iteration kernels (one HBM pass per iteration instead of two).
+//
+//   MODE_CHEBY  run_cheby_iterate (kernel_interface.cpp:258-271) = cheby_iterate (cheby.cpp:73-110)
+//               then cheby_calc_u (:46-70):   s = A u ; r = u0 - s ; p = alpha p + beta r ; u += p
+//               reads u(stencil), u0, p, kx, ky; writes r, p, u'      = 64 B/cell (unfused: 64 + 24)
+//   MODE_PPCG   run_ppcg_inner_iteration (kernel_interface.cpp:314-328) = ppcg_calc_ur (ppcg.cpp:34-66)
+//               then ppcg_calc_sd (:69-94):   s = A sd ; r -= s ; u += sd ; sd = alpha sd + beta r
+//               reads sd(stencil), r, u, kx, ky; writes r, u, sd'     = 64 B/cell (unfused: 56 + 24)
+//
+// The stencil operand (u resp. sd) is updated in the same pass, so it is double buffered: reads come
+// from a_in, the updated operand goes to a_out and the chunk swaps the two buffers.  Reflective
+// boundaries of external faces are applied by index mirroring (what halo_update_driver's local update
+// would have put in the halo), so no halo kernel runs between iterations on a single chunk; internal
+// faces read the exchanged halo.  Same operations in the same order as the two reference kernels:
+// results are bit-identical.  `w` (= A u) is never read in the Chebyshev phase and is not stored here.
+enum { MODE_CHEBY = 0, MODE_PPCG = 1 };
+template <int MODE, int U>
+__global__ void __launch_bounds__(TL_TPB)
+k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_out, double* __restrict__ f1,
+                const double* f2_in, double* f2_out, const double* __restrict__ kx, const double* __restrict__ ky,
+                double alpha, double beta, int rows, int rev, int ext_mask)
+{
+    // MODE_CHEBY: f1 = p (in/out), f2_in = u0 (read), f2_out = r (written)
+    // MODE_PPCG : f1 = r (in/out), f2_in = f2_out = u (in/out)
+    const HotTile t = hot_tile(g, rows, rev);
+    if (!t.v0) return;
+    const long pitch = g.pitch;
+    const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
+    const int dl = ((ext_mask & 1) && t.kk == klo) ? 0 : -1;         // left neighbour of cell 0 (mirrored: itself)
+    const int dr = ((ext_mask & 2) && t.kk + 1 == khi) ? 1 : 2;      // right neighbour of cell 1
+    const bool mir_r0 = (ext_mask & 2) && t.kk == khi;               // cell 0 is the last column
+    long i = t.i;
+    const long im = ((ext_mask & 4) && t.j0 == jlo) ? i : i - pitch;
+    double2 am = ld2_ro(a_in + im);
+    double2 ac = ld2_ro(a_in + i);
+    double al = __ldg(a_in + i + dl), ar = __ldg(a_in + i + dr);
+    double2 kyc = ld2_ro(ky + i);
+    for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+        double2 an[U], kyn[U], kxc[U], x1[U], x2[U];
+        double kxr[U], aln[U], arn[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                const long iq = i + q * pitch;
+                const long in = ((ext_mask & 8) && jb + q == jhi) ? iq : iq + pitch;
+                an[q] = ld2_ro(a_in + in);
+                aln[q] = __ldg(a_in + in + dl);
+                arn[q] = __ldg(a_in + in + dr);
+                kyn[q] = ld2_ro(ky + iq + pitch);
+                kxc[q] = ld2_ro(kx + iq);
+                kxr[q] = __ldg(kx + iq + 2);
+                x1[q] = ld2(f1 + iq);
+                x2[q] = ld2(f2_in + iq);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                const long iq = i + q * pitch;
+                double2 sv;
+                sv.x = smvp(kxc[q].x, kxc[q].y, kyc.x, kyn[q].x, ac.x, al, mir_r0 ? ac.x : ac.y, am.x, an[q].x);
+                sv.y = smvp(kxc[q].y, kxr[q], kyc.y, kyn[q].y, ac.y, ac.x, ar, am.y, an[q].y);
+                double2 o1, o2, ao;
+                if (MODE == MODE_CHEBY) {
+                    // x1 = p, x2 = u0:  r = u0 - s ; p = alpha p + beta r ; u' = u + p
+                    o2.x = x2[q].x - sv.x;
+                    o2.y = x2[q].y - sv.y;
+                    o1.x = alpha * x1[q].x + beta * o2.x;
+                    o1.y = alpha * x1[q].y + beta * o2.y;
+                    ao.x = ac.x + o1.x;
+                    ao.y = ac.y + o1.y;
+                } else {
+                    // x1 = r, x2 = u:  r -= s ; u += sd ; sd' = alpha sd + beta r
+                    o1.x = x1[q].x - sv.x;
+                    o1.y = x1[q].y - sv.y;
+                    o2.x = x2[q].x + ac.x;
+                    o2.y = x2[q].y + ac.y;
+                    ao.x = alpha * ac.x + beta * o1.x;
+                    ao.y = alpha * ac.y + beta * o1.y;
+                }
+                st_pair(f1 + iq, o1, t.v1);
+                st_pair(f2_out + iq, o2, t.v1);
+                st_pair(a_out + iq, ao, t.v1);
+                am = ac; ac = an[q]; kyc = kyn[q]; al = aln[q]; ar = arn[q];
+            }
+        }
+    }
+}
+
+static int alt_buffer(tl_chunk* c, int field)
+{
+    if (!c->alt_alloc[field]) {
+        TL_CUDA(cudaMalloc((void**)&c->alt_alloc[field], c->field_elems * sizeof(double)));
+        TL_CUDA(cudaMemsetAsync(c->alt_alloc[field], 0, c->field_elems * sizeof(double), c->stream));
+        c->alt[field] = c->alt_alloc[field];
+    }
+    return TL_OK;
+}
+
+// Runs one fused iteration and swaps the operand's two buffers (field = TL_FIELD_U or TL_FIELD_SD).
+static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta)
+{
+    const int field = (mode == MODE_CHEBY) ? TL_FIELD_U : TL_FIELD_SD;
+    TL_TRY(alt_buffer(c, field));
+    const int rows = tile_rows(c, TUNE_W);
+    dim3 grid = hot_grid(c, rows);
+    const int mask = external_mask(c);
+    if (mode == MODE_CHEBY)
+        k_fused_stencil<MODE_CHEBY, 2><<<grid, TL_TPB, 0, c->stream>>>(
+            c->g, c->f[TL_FIELD_U], c->alt[TL_FIELD_U], c->f[TL_FIELD_P], c->f[TL_FIELD_U0], c->f[TL_FIELD_R],
+            c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask);
+    else
+        k_fused_stencil<MODE_PPCG, 2><<<grid, TL_TPB, 0, c->stream>>>(
+            c->g, c->f[TL_FIELD_SD], c->alt[TL_FIELD_SD], c->f[TL_FIELD_R], c->f[TL_FIELD_U], c->f[TL_FIELD_U],
+            c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    double* tmp = c->f[field];
+    c->f[field] = c->alt[field];
+    c->alt[field] = tmp;
+    return TL_OK;
+}
+int tlk_cheby_fused(tl_chunk* c, double alpha, double beta) { return launch_fused_stencil(c, MODE_CHEBY, alpha, beta); }
+int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta) { return launch_fused_stencil(c, MODE_PPCG, alpha, beta); }
+
+// Puts a double-buffered field back into its slab position (copy if it currently lives in the
+// alternate buffer), so that slab-relative peer mappings and later phases see it where they expect.
+int tlk_field_home(tl_chunk* c, int field)
+{
+    double* home = c->slab + (size_t)field * c->field_elems;
+    if (c->f[field] == home) return TL_OK;
+    TL_CUDA(cudaMemcpyAsync(home, c->f[field], c->field_elems * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    if (field == TL_FIELD_P) c->p2 = c->f[field];
+    else c->alt[field] = c->f[field];
+    c->f[field] = home;
+    return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Chebyshev (cheby.cpp), PPCG (ppcg.cpp), Jacobi (jacobi.cpp), shared solver kernels
 // ---------------------------------------------------------------------------------------------
 // cheby.cpp:7-43

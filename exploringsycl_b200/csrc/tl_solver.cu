@@ -504,6 +504,7 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
     TL_TRY(cg_presteps(c, k, o, fields, &rro, &error, &tt, &ended, &launches));
     int num_cheby_iters = 0, est_iterations = 0;
     double theta = 0.0;
+    const bool fused = o->fuse_p_into_w != 0;
     if (!ended) {
         for (; tt < o->max_iters; ++tt) {
             num_cheby_iters++;
@@ -526,9 +527,14 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
                 calc_2norm = (num_cheby_iters >= est_iterations) && ((tt + 1) % 10 == 0);
             }
             // cheby_main_step_driver, cheby_driver.c:110-143
-            TL_TRY(tlk_cheby_iterate(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters]));
-            TL_TRY(tlk_cheby_calc_u(c));
-            launches += 2;
+            if (fused) { // one pass: cheby_iterate + cheby_calc_u, u double buffered
+                TL_TRY(tlk_cheby_fused(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters]));
+                launches += 1;
+            } else {
+                TL_TRY(tlk_cheby_iterate(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters]));
+                TL_TRY(tlk_cheby_calc_u(c));
+                launches += 2;
+            }
             if (calc_2norm) TL_TRY(norm2(c, k, TL_FIELD_R, &error));
             if (num_cheby_iters == 1) {
                 // cheby_calc_est_iterations, cheby_driver.c:146-160 (float logf/roundf as written)
@@ -537,8 +543,14 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
                 const double gamm = (sqrt(cn) - 1.0) / (sqrt(cn) + 1.0);
                 est_iterations = (int)roundf(logf(it_alpha) / (2.0 * logf(gamm)));
             }
-            TL_TRY(tl_halo_update(c, k, fields, 1));
+            // On one chunk the fused kernel applies the reflective boundary by mirroring: u's halo is only
+            // materialised once, after the loop.
+            if (!(fused && !multi)) TL_TRY(tl_halo_update(c, k, fields, 1));
             if (fabs(error) < o->eps) break;
+        }
+        if (fused) {
+            TL_TRY(tlk_field_home(c, TL_FIELD_U));
+            if (!multi && num_cheby_iters > 0) TL_TRY(tl_halo_update(c, k, fields, 1));
         }
     }
     info->iters_a = tt - num_cheby_iters + 1; // cheby_driver.c:73
@@ -564,6 +576,7 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
     TL_TRY(cg_presteps(c, k, o, fields, &rro, &error, &tt, &ended, &launches));
     int num_ppcg_iters = 0;
     double theta = 0.0;
+    const bool fused = o->fuse_p_into_w != 0;
     if (!ended) {
         for (; tt < o->max_iters; ++tt) {
             num_ppcg_iters++;
@@ -590,11 +603,16 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
             fields_reset(fields);
             fields[TL_FIELD_SD] = 1;
             for (int pp = 0; pp < o->ppcg_inner_steps; ++pp) {
-                TL_TRY(tl_halo_update(c, k, fields, 1));
-                TL_TRY(tlk_ppcg_calc_ur(c));
-                TL_TRY(tlk_ppcg_calc_sd(c, c->cheby_alphas[pp], c->cheby_betas[pp]));
+                if (fused) { // one pass: ppcg_calc_ur + ppcg_calc_sd, sd double buffered, boundary by mirroring
+                    if (multi) TL_TRY(tl_halo_update(c, k, fields, 1));
+                    TL_TRY(tlk_ppcg_fused(c, c->cheby_alphas[pp], c->cheby_betas[pp]));
+                } else {
+                    TL_TRY(tl_halo_update(c, k, fields, 1));
+                    TL_TRY(tlk_ppcg_calc_ur(c));
+                    TL_TRY(tlk_ppcg_calc_sd(c, c->cheby_alphas[pp], c->cheby_betas[pp]));
+                }
             }
-            launches += 3 + 2 * o->ppcg_inner_steps;
+            launches += 3 + (fused ? 1 : 2) * o->ppcg_inner_steps;
             fields_reset(fields);
             fields[TL_FIELD_P] = 1;
             double rrn = 0.0;
@@ -607,6 +625,7 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
             if (fabs(error) < o->eps) break;
         }
     }
+    if (fused) TL_TRY(tlk_field_home(c, TL_FIELD_SD));
     info->iters_a = tt - num_ppcg_iters + 1; // ppcg_driver.c:59
     info->iters_b = num_ppcg_iters;
     info->total_iters = (tt < o->max_iters) ? tt + 1 : tt;
@@ -759,7 +778,7 @@ extern "C" int tl_timestep_host(tl_chunk* c, tl_comms* k, const tl_solve_opts* o
 // Kernel micro-benchmark hook (bench.py roofline leg).  Uses the current field contents.
 extern "C" int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_launch)
 {
-    TL_CHECK_ARG(c && ms_per_launch && reps > 0 && which >= 0 && which <= 3, "bad arguments");
+    TL_CHECK_ARG(c && ms_per_launch && reps > 0 && which >= 0 && which <= 17, "bad arguments");
     TL_CUDA(cudaSetDevice(c->device));
     cudaEvent_t e0, e1;
     TL_CUDA(cudaEventCreate(&e0));
@@ -774,7 +793,21 @@ extern "C" int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_l
             if (which == 0) TL_TRY(tlk_cg_calc_w(c, SCAL_IMM, false));
             else if (which == 1) TL_TRY(tlk_cg_calc_ur(c, SCAL_IMM, 1e-9, false));
             else if (which == 2) TL_TRY(tlk_cg_calc_p(c, SCAL_IMM, 0.5, false, false));
-            else TL_TRY(tlk_cg_calc_pw(c, false));
+            else if (which == 3) TL_TRY(tlk_cg_calc_pw(c, false));
+            else if (which == 4) TL_TRY(tlk_cheby_iterate(c, 0.5, 0.25));
+            else if (which == 5) TL_TRY(tlk_cheby_calc_u(c));
+            else if (which == 6) TL_TRY(tlk_ppcg_calc_ur(c));
+            else if (which == 7) TL_TRY(tlk_ppcg_calc_sd(c, 0.5, 0.25));
+            else if (which == 8) TL_TRY(tlk_jacobi_iterate(c));
+            else if (which == 9) TL_TRY(tlk_calculate_residual(c));
+            else if (which == 10) TL_TRY(tlk_calculate_2norm(c, TL_FIELD_R));
+            else if (which == 11) TL_TRY(tlk_field_summary(c));
+            else if (which == 12) TL_TRY(tlk_cg_init(c, TL_CONDUCTIVITY, 0.5, 0.5));
+            else if (which == 13) TL_TRY(tlk_finalise(c));
+            else if (which == 14) TL_TRY(tlk_copy_field(c, TL_FIELD_U0, TL_FIELD_U, true));
+            else if (which == 15) TL_TRY(tlk_cheby_init(c, 2.0));
+            else if (which == 16) TL_TRY(tlk_cheby_fused(c, 0.5, 0.25));
+            else TL_TRY(tlk_ppcg_fused(c, 0.5, 0.25));
         }
         if (pass) TL_CUDA(cudaEventRecord(e1, c->stream));
     }

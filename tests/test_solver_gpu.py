@@ -207,3 +207,26 @@ def test_bm5_4000_full_deck_matches_reference_goldens():
     assert abs(calls - 42297) <= 10, calls  # +-1 per step from the reduction order
     assert rel(summary["vol"], 100.0) < 1e-12 and rel(summary["mass"], 8401.6) < 1e-12
     print("bm5: calls", calls, "temp", repr(summary["temp"]), "iters", [h["iters_a"] for h in hist])
+
+
+@pytest.mark.parametrize("name,sid", [("cheby", O.CHEBY), ("ppcg", O.PPCG)])
+def test_fused_cheby_ppcg_iterations_are_bit_identical(name, sid):
+    """One-pass Chebyshev (iterate + calc_u) and PPCG (calc_ur + calc_sd) kernels == the two-kernel
+    sequences of kernel_interface.cpp:258-271 / :314-328, bit for bit."""
+    from exploringsycl_b200 import TeaLeaf, read_config
+    res = []
+    for fused in (0, 1):
+        s, states = read_config(os.path.join(DECKS, "tea_250_%s.in" % name))
+        s.end_step = 3
+        s.fuse_p_into_w = fused
+        app = TeaLeaf(s, states)
+        summary = app.diffuse()
+        res.append((summary, [(h["iters_a"], h["iters_b"], h["error"]) for h in app.history],
+                    {f: app.chunk.read(f) for f in (3, 4, 7, 2, 5)}))
+        app.close()
+    assert res[0][1] == res[1][1]
+    assert res[0][0] == res[1][0]
+    for f in res[0][2]:
+        assert np.array_equal(res[0][2][f][2:-2, 2:-2], res[1][2][f][2:-2, 2:-2]), f
+    # u's halo is materialised at the end of the fused phase exactly as the per-iteration updates leave it
+    assert np.array_equal(res[0][2][3][1:-1, 1:-1], res[1][2][3][1:-1, 1:-1])
