@@ -156,6 +156,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--mesh", type=int, nargs=2, default=None)
+    ap.add_argument("--solver", default="cg", choices=["cg", "cheby", "ppcg", "jacobi"],
+                    help="non-default solvers are reported under their own metric name (BASELINE configs[3])")
+    ap.add_argument("--max-iters", type=int, default=10000)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -206,7 +209,12 @@ def main():
     if world > 1:
         session = "bench_%s" % os.environ.get("MASTER_PORT", "0")
         comms = Comms(session, rank, world, device=local_rank)
-    s, states = deck_settings(nx, ny)
+    s, states = deck_settings(nx, ny, args.max_iters)
+    s.solver = {"jacobi": 0, "cg": 1, "cheby": 2, "ppcg": 3}[args.solver]
+    inner = s.ppcg_inner_steps if args.solver == "ppcg" else 0
+
+    def matvecs(info):  # solver-loop iterations (+ the reduction-free inner steps of PPCG)
+        return info.total_iters + info.iters_b * inner
     if os.environ.get("TL_BENCH_FUSED") is not None:
         s.fuse_p_into_w = int(os.environ["TL_BENCH_FUSED"])
     app = TeaLeaf(s, states, comms, device=local_rank)
@@ -226,8 +234,8 @@ def main():
     per_step = []
     for tt in range(args.steps):
         info = app.solve(args.warmup + tt)
-        iters += info.total_iters
-        per_step.append(info.iters_a)
+        iters += matvecs(info)
+        per_step.append(info.iters_a if args.solver in ("cg", "jacobi") else [info.iters_a, info.iters_b])
     ms = C.c_double()
     check(L.tl_timer_stop(ch.handle, C.byref(ms)))
     barrier()
@@ -257,7 +265,7 @@ def main():
         for tt in range(args.steps):
             check(L.tl_timestep_host(ch.handle, comms.handle if comms else None, C.byref(o), s.dt_init, s.dx,
                                      s.dy, hd_p, he_p, C.byref(info), C.byref(summ)))
-            e_iters += info.total_iters
+            e_iters += matvecs(info)
         barrier()
         e_wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": cells * e_iters / e_wall, "unit": "cell-iter/s",
@@ -315,13 +323,14 @@ def main():
                    nx, ny, cap, w)}
 
     if rank == 0:
-        line = {"metric": "CG cell-iterations/s", "value": value, "unit": "cell-iter/s", "n_gpus": n_gpus,
+        metric = {"cg": "CG", "cheby": "Chebyshev", "ppcg": "PPCG (outer+inner)", "jacobi": "Jacobi"}[args.solver]
+        line = {"metric": metric + " cell-iterations/s", "value": value, "unit": "cell-iter/s", "n_gpus": n_gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * gpu_s / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "TeaLeaf CG fp64 %dx%d, standard 5-state deck (tea_bm_5 geometry), "
+                "config": {"workload": "TeaLeaf %s fp64 %dx%d, standard 5-state deck (tea_bm_5 geometry), "
                                        "eps 1e-15, one timestep per step, %s" % (
-                                           nx, ny, "1 GPU" if n_gpus == 1 else
+                                           metric, nx, ny, "1 GPU" if n_gpus == 1 else
                                            "%d GPUs %dx%d chunks" % (n_gpus, app.decomposition["x_chunks"],
                                                                      app.decomposition["y_chunks"])),
                            "cells_per_gpu": cells // n_gpus, "cg_iterations_per_step": per_step,

@@ -90,7 +90,6 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
     memset(c->scal_h, 0, 3 * sizeof(DevScal));
     TL_TRY(dev_zalloc(&c->d_alphas, max_iters + 1));
     TL_TRY(dev_zalloc(&c->d_betas, max_iters + 1));
-    TL_TRY(dev_zalloc(&c->d_cheby, 2 * (size_t)max_iters + 2));
     // kernel_initialise.cpp:76-79: host coefficient arrays of max_iters doubles, zeroed
     c->cg_alphas = (double*)calloc(max_iters + 1, sizeof(double));
     c->cg_betas = (double*)calloc(max_iters + 1, sizeof(double));
@@ -102,7 +101,6 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
         TL_TRY(dev_zalloc(&c->face_send[fc], c->face_elems));
         TL_TRY(dev_zalloc(&c->face_recv[fc], c->face_elems));
     }
-    TL_CUDA(cudaMallocHost((void**)&c->h_stage, c->face_elems * sizeof(double)));
     TL_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     TL_CUDA(cudaEventCreate(&c->ev0));
     TL_CUDA(cudaEventCreate(&c->ev1));
@@ -122,10 +120,9 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
         if (c->alt_alloc[f]) cudaFree(c->alt_alloc[f]);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->scal); cudaFreeHost(c->scal_h);
-    cudaFree(c->d_alphas); cudaFree(c->d_betas); cudaFree(c->d_cheby);
+    cudaFree(c->d_alphas); cudaFree(c->d_betas);
     free(c->cg_alphas); free(c->cg_betas); free(c->cheby_alphas); free(c->cheby_betas);
     for (int fc = 0; fc < 4; ++fc) { cudaFree(c->face_send[fc]); cudaFree(c->face_recv[fc]); }
-    cudaFreeHost(c->h_stage);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->stream);
     delete c;

@@ -508,22 +508,25 @@ int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth)
         const int f0 = phase ? TL_FACE_BOTTOM : TL_FACE_LEFT;
         const unsigned long long seq = ++k->xchg_seq;
         const int par = (int)(seq & 1ull);
-        for (int f = f0; f < f0 + 2; ++f) {
-            if (c->nb[f] == TL_EXTERNAL_FACE) continue;
-            int len = 0;
-            TL_TRY(tlk_pack_face(c, fields, depth, f, true, c->nb_recv[f] + (size_t)par * k->face_elems, &len));
-            k_signal<<<1, 1, 0, c->stream>>>(c->nb_flag[f], seq);
-            ++g_tl_launches;
+        int faces[2];
+        double* sbuf[2];
+        double* rbuf[2];
+        unsigned long long* sflag[2];
+        unsigned long long* rflag[2];
+        for (int q = 0; q < 2; ++q) {
+            const int f = f0 + q;
+            const bool has = (c->nb[f] != TL_EXTERNAL_FACE);
+            faces[q] = has ? f : -1;
+            sbuf[q] = has ? c->nb_recv[f] + (size_t)par * k->face_elems : nullptr;
+            sflag[q] = has ? c->nb_flag[f] : nullptr;
+            rbuf[q] = has ? k->arena + arena_recv_off(k, f, par) : nullptr;
+            rflag[q] = has ? (unsigned long long*)(k->arena + arena_flags_off(k)) + f : nullptr;
         }
-        for (int f = f0; f < f0 + 2; ++f) {
-            if (c->nb[f] == TL_EXTERNAL_FACE) continue;
-            unsigned long long* my_flag = (unsigned long long*)(k->arena + arena_flags_off(k)) + f;
-            k_wait<<<1, 1, 0, c->stream>>>(my_flag, seq, c->scal);
-            ++g_tl_launches;
-            int len = 0;
-            TL_TRY(tlk_pack_face(c, fields, depth, f, false, k->arena + arena_recv_off(k, f, par), &len));
-        }
-        TL_CUDA(cudaGetLastError());
+        if (faces[0] < 0 && faces[1] < 0) continue;
+        // pack both faces of the phase into the neighbours' buffers + release their flags: one launch;
+        // acquire my flags + unpack: one launch (remote_halo_driver.c:24-126 order: L/R done before B/T packs)
+        TL_TRY(tlk_phase_exchange(c, fields, depth, true, faces, sbuf, sflag, seq));
+        TL_TRY(tlk_phase_exchange(c, fields, depth, false, faces, rbuf, rflag, seq));
     }
     return TL_OK;
 }

@@ -37,7 +37,6 @@ struct DevScal {
     int conv_iter;     // multi-rank loop: iterations >= conv_iter are no-ops (INT_MAX while running)
     int conv_mode;     // 0: sqrt(|rrn|) < eps (cg_driver.c:24); 1: |rrn| < eps (cheby_driver.c:70)
     unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
-    unsigned int seq;        // reduction sequence number (multi-GPU slot parity)
     unsigned int pad;        // 0xdead: a peer wait timed out
     unsigned long long dbg[4]; // first timed-out wait: site, wanted value, seen value, block id
 };
@@ -91,15 +90,10 @@ struct tl_chunk {
     DevScal* scal_h;              // pinned host mirror [0] + two polling snapshots [1],[2]
     double* d_alphas;             // device cg_alphas / cg_betas written by the resident loop
     double* d_betas;
-    double* d_cheby;              // device copy of cheby alphas/betas (2*max_iters)
     double *cg_alphas, *cg_betas, *cheby_alphas, *cheby_betas; // host (reference host reads/writes)
     double* face_send[4];         // device staging, 6 fields * hd * max(x,y)
     double* face_recv[4];
-    unsigned long long* face_flags; // device: arrival counters per face [4] (+ scalar flags)
-    double* red_slots;            // device: [2][TL_MAX_PEERS] all-reduce slots
-    unsigned long long* red_flags;// device: [2][TL_MAX_PEERS]
     size_t face_elems;
-    double* h_stage;              // pinned host staging for the host-buffer pack/unpack API
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     tl_comms* comms;              // non-null once attached
@@ -137,8 +131,6 @@ extern long g_tl_launches;
 // Scalar sources for the solver kernels: either an immediate (host-driven plugin API) or the
 // device-resident DevScal (resident loop).
 enum ScalMode { SCAL_IMM = 0, SCAL_DEV = 1 };
-// Reduction destinations inside DevScal for the tail CTA
-enum RedKind { RED_PW = 0, RED_RRN, RED_RRO_INIT, RED_NORM, RED_JACOBI, RED_SUMMARY, RED_BB };
 
 int tlk_set_chunk_data(tl_chunk* c, double x_min, double y_min, double dx, double dy);
 int tlk_set_initial_state(tl_chunk* c, double energy, double density);
@@ -147,6 +139,8 @@ int tlk_copy_field(tl_chunk* c, int dst, int src, bool interior_only);
 int tlk_field_summary(tl_chunk* c);                       // -> scal->sums[0..3]
 int tlk_local_halos(tl_chunk* c, const int fields[6], int depth);
 int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len);
+int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, const int faces[2], double* const bufs[2],
+                       unsigned long long* const flags[2], unsigned long long seq);
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr);                // -> scal->pw (& alpha when SCAL_DEV)
 int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false); // -> scal->rrn (& beta, conv when SCAL_DEV)

@@ -33,6 +33,44 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// system-scope flag primitives of the NVLink paths (halo exchange, resident multi-rank CG loop)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU: on timeout an
+// error mark is left in DevScal.pad and the caller carries on with whatever is there.
+__device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
+                                          unsigned long long site = 0)
+{
+    const long long t0 = clock64();
+    unsigned long long seen;
+    while ((seen = ld_acquire_sys(flag)) < want) {
+        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
+        if (clock64() - t0 > 20000000000LL) { // ~10 s
+            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
+                S->dbg[0] = site;
+                S->dbg[1] = want;
+                S->dbg[2] = seen;
+                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
+            }
+            break;
+        }
+        __nanosleep(64);
+    }
+}
 struct RedArgs {
     double* partials; // [NR][cap]
     int cap;
@@ -360,6 +398,102 @@ int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pa
     return TL_OK;
 }
 
+// One launch per exchange phase and direction: both faces of a phase (L+R or B+T) and all flagged fields.
+//   k_pack_send   : gathers into the NEIGHBOUR's receive buffer (peer-mapped, NVLink stores); the last CTA
+//                   to finish releases the neighbours' arrival flags (every CTA fences its stores first).
+//   k_wait_unpack : thread 0 of each CTA acquires its face's arrival flag, then the CTA scatters.
+struct PhaseFaces {
+    int face[2];                  // TL_FACE_* or -1
+    double* buf[2];               // pack: neighbour's receive buffer; unpack: my receive buffer
+    unsigned long long* flag[2];  // pack: neighbour's arrival flag;   unpack: my arrival flag
+};
+
+__device__ __forceinline__ long halo_cell_index(const Geo& g, int face, int depth, int pack, int b)
+{
+    const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+    int jj, kk;
+    if (lr) {
+        jj = b / depth;
+        const int d = b % depth;
+        if (face == TL_FACE_LEFT) kk = pack ? g.hd + d : g.hd - depth + d;
+        else kk = pack ? g.x - g.hd - depth + d : g.x - g.hd + d;
+    } else {
+        const int d = b / g.x;
+        kk = b % g.x;
+        if (face == TL_FACE_TOP) jj = pack ? g.y - g.hd - depth + d : g.y - g.hd + d;
+        else jj = pack ? g.hd + d : g.hd - depth + d;
+    }
+    return (long)g.off + (long)jj * g.pitch + kk;
+}
+
+__global__ void k_pack_send(Geo g, FieldList fl, int depth, PhaseFaces pf, unsigned long long seq, DevScal* S)
+{
+    const int face = pf.face[blockIdx.z];
+    if (face >= 0) {
+        const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+        const int per_field = depth * (lr ? g.y : g.x);
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b < per_field)
+            pf.buf[blockIdx.z][(size_t)blockIdx.y * per_field + b] =
+                fl.f[blockIdx.y][halo_cell_index(g, face, depth, 1, b)];
+    }
+    __shared__ int s_last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        s_last = (atomicAdd(&S->counter[2], 1u) == total - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 2) {
+        if (threadIdx.x == 0) S->counter[2] = 0u;
+        if (pf.face[threadIdx.x] >= 0) st_release_sys(pf.flag[threadIdx.x], seq);
+    }
+}
+
+__global__ void k_wait_unpack(Geo g, FieldList fl, int depth, PhaseFaces pf, unsigned long long seq, DevScal* S)
+{
+    const int face = pf.face[blockIdx.z];
+    if (face < 0) return;
+    if (threadIdx.x == 0) spin_flag(pf.flag[blockIdx.z], seq, S, 50ull + face);
+    __syncthreads();
+    const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+    const int per_field = depth * (lr ? g.y : g.x);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < per_field)
+        fl.f[blockIdx.y][halo_cell_index(g, face, depth, 0, b)] =
+            __ldcg(pf.buf[blockIdx.z] + (size_t)blockIdx.y * per_field + b);
+}
+
+// faces/bufs/flags: two entries (one per face of the phase; face -1 = no neighbour on that side)
+int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, const int faces[2], double* const bufs[2],
+                       unsigned long long* const flags[2], unsigned long long seq)
+{
+    FieldList fl;
+    fl.n = 0;
+    for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i)
+        if (fields[i]) fl.f[fl.n++] = c->f[i];
+    if (!fl.n || (faces[0] < 0 && faces[1] < 0)) return TL_OK;
+    PhaseFaces pf;
+    int per_field = 0;
+    for (int q = 0; q < 2; ++q) {
+        pf.face[q] = faces[q];
+        pf.buf[q] = bufs[q];
+        pf.flag[q] = flags[q];
+        if (faces[q] >= 0) {
+            const bool lr = (faces[q] == TL_FACE_LEFT || faces[q] == TL_FACE_RIGHT);
+            const int n = depth * (lr ? c->g.y : c->g.x);
+            per_field = n > per_field ? n : per_field;
+        }
+    }
+    dim3 grid((per_field + 127) / 128, fl.n, 2);
+    if (send) k_pack_send<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, seq, c->scal);
+    else k_wait_unpack<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, seq, c->scal);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // CG
 // ---------------------------------------------------------------------------------------------
@@ -423,6 +557,7 @@ __global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
     S->dbg[0] = S->dbg[1] = S->dbg[2] = S->dbg[3] = 0ull;
     S->counter[0] = 0u;
     S->counter[1] = 0u;
+    S->counter[2] = 0u;
 }
 int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
 {
@@ -436,43 +571,6 @@ int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
 // ---------------------------------------------------------------------------------------------
 // Multi-rank helpers of the resident CG loop (see MultiCtx in tl_internal.h)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU: on timeout an
-// error mark is left in DevScal.pad and the caller carries on with whatever is there.
-__device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
-                                          unsigned long long site = 0)
-{
-    const long long t0 = clock64();
-    unsigned long long seen;
-    while ((seen = ld_acquire_sys(flag)) < want) {
-        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
-        if (clock64() - t0 > 20000000000LL) { // ~10 s
-            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
-                S->dbg[0] = site;
-                S->dbg[1] = want;
-                S->dbg[2] = seen;
-                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
-            }
-            break;
-        }
-        __nanosleep(64);
-    }
-}
 // Sum of the N ranks' partials of (kind, local iteration tl) in rank order.  Called by ALL 32 lanes of
 // warp 0: lane r waits for rank r's flag and loads its partial (the N memory latencies overlap), then
 // the partials are added in rank order, identically on every rank (same order as tl_comms_sum).
@@ -590,10 +688,16 @@ static int tile_rows(const tl_chunk* c, int kernel)
 {
     if (g_rows[kernel] > 0) return g_rows[kernel];
     if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
+    // Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read), but the tile
+    // count should sit just under 8 CTAs per SM so the whole grid is one balanced wave
+    // (profiles/tuning_r01.txt: 4000x4000 -> 55 rows, 1168 CTAs on 148 SMs).
     const int colb = (c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS;
-    for (int rows = 64; rows > 8; rows >>= 1)
-        if ((long)colb * ((c->ny + rows - 1) / rows) >= 6 * 148) return rows; // >= 6 CTAs per SM
-    return 8;
+    int rowblocks = (8 * 148) / colb;
+    if (rowblocks < 1) rowblocks = 1;
+    int rows = (c->ny + rowblocks - 1) / rowblocks;
+    if (rows < 8) rows = 8;
+    if (rows > 128) rows = 128;
+    return rows;
 }
 static dim3 hot_grid(const tl_chunk* c, int rows)
 {
