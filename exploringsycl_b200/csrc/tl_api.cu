@@ -84,6 +84,10 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
     TL_TRY(dev_zalloc(&c->vertex_y, g.y + 2));
     c->partial_cap = ((g.x + TL_TPB - 1) / TL_TPB) * ((g.y + 7) / 8) + 64;
     TL_TRY(dev_zalloc(&c->partials, (size_t)c->partial_cap * 4));
+    c->gpartial_cap = c->partial_cap / 64 + 2;
+    TL_TRY(dev_zalloc(&c->gpartials, (size_t)c->gpartial_cap * 4));
+    TL_CUDA(cudaMalloc((void**)&c->gcount, sizeof(unsigned int) * c->gpartial_cap));
+    TL_CUDA(cudaMemset(c->gcount, 0, sizeof(unsigned int) * c->gpartial_cap));
     TL_CUDA(cudaMalloc((void**)&c->scal, sizeof(DevScal)));
     TL_CUDA(cudaMemset(c->scal, 0, sizeof(DevScal)));
     TL_CUDA(cudaMallocHost((void**)&c->scal_h, 3 * sizeof(DevScal)));
@@ -119,7 +123,7 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     for (int f = 0; f < TL_NUM_FIELDS; ++f)
         if (c->alt_alloc[f]) cudaFree(c->alt_alloc[f]);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
-    cudaFree(c->partials); cudaFree(c->scal); cudaFreeHost(c->scal_h);
+    cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas);
     free(c->cg_alphas); free(c->cg_betas); free(c->cheby_alphas); free(c->cheby_betas);
     for (int fc = 0; fc < 4; ++fc) { cudaFree(c->face_send[fc]); cudaFree(c->face_recv[fc]); }

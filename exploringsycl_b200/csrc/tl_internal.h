@@ -86,6 +86,9 @@ struct tl_chunk {
     double* alt_alloc[TL_NUM_FIELDS];
     double* partials;             // device, per-tile partial sums (4 lanes)
     int partial_cap;              // tiles
+    double* gpartials;            // device, per-group (64 tiles) sums (4 lanes)
+    unsigned int* gcount;         // device, per-group arrival tickets
+    int gpartial_cap;
     DevScal* scal;                // device
     DevScal* scal_h;              // pinned host mirror [0] + two polling snapshots [1],[2]
     double* d_alphas;             // device cg_alphas / cg_betas written by the resident loop

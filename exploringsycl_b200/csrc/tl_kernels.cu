@@ -72,21 +72,30 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
     }
 }
 struct RedArgs {
-    double* partials; // [NR][cap]
-    int cap;
+    double* partials;   // [NR][cap]   one per tile
+    double* gpartials;  // [NR][gcap]  one per group of TL_RED_GROUP tiles
+    unsigned int* gcount; // [gcap]    arrival tickets per group (self-resetting)
+    int cap, gcap;
     DevScal* S;
 };
+#define TL_RED_GROUP 64
 
-// Deterministic single-pass grid reduction.  Every CTA writes its NR tile partials; the CTA that
-// takes the last ticket sums all tile partials in a fixed order.  Returns true in EVERY thread of
-// that last CTA with the totals in `tot` (callers do their scalar bookkeeping in thread 0).
+// Deterministic single-pass grid reduction, two levels.  Every CTA writes its NR tile partials.  Tiles
+// are grouped by index (64 per group): the last CTA of a group to arrive adds that group's partials in
+// a fixed order -- this happens while the rest of the grid is still streaming -- and the last group to
+// finish adds the group sums, again in a fixed order.  The serial tail after the last tile is therefore
+// ~ntiles/64 values instead of ntiles.  The result does not depend on arrival order.
+// Returns true in EVERY thread of the final CTA with the totals in `tot`.
 template <int NR>
 __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
                                             double (&tot)[NR])
 {
     __shared__ double sm[NR][TL_TPB / 32];
-    __shared__ int s_last;
+    __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int group = tile / TL_RED_GROUP;
+    const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
+    const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         double v = warp_sum(acc[r]);
@@ -100,18 +109,38 @@ __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra
             __stcg(&ra.partials[(size_t)r * ra.cap + tile], v);
         }
         __threadfence();
-        unsigned int t = atomicAdd(&ra.S->counter[0], 1u);
-        s_last = (t == (unsigned int)(ntiles - 1));
+        s_flag = (atomicAdd(&ra.gcount[group], 1u) == (unsigned int)(gsize - 1));
     }
     __syncthreads();
-    if (!s_last) return false;
+    if (!s_flag) return false;
+    // last CTA of this group: group sum (lanes of warps 0,1 hold one tile partial each)
     __threadfence();
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-        const double* src = ra.partials + (size_t)r * ra.cap;
+        double v = 0.0;
+        if (tid < gsize) v = __ldcg(ra.partials + (size_t)r * ra.cap + group * TL_RED_GROUP + tid);
+        v = warp_sum(v);
+        __syncthreads();
+        if (lane == 0) sm[r][wid] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) __stcg(&ra.gpartials[(size_t)r * ra.gcap + group], sm[r][0] + sm[r][1]);
+        ra.gcount[group] = 0u;
+        __threadfence();
+        s_flag = (atomicAdd(&ra.S->counter[0], 1u) == (unsigned int)(ngroups - 1));
+    }
+    __syncthreads();
+    if (!s_flag) return false;
+    // last group: total
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const double* src = ra.gpartials + (size_t)r * ra.gcap;
         double s = 0.0;
-#pragma unroll 8
-        for (int k = tid; k < ntiles; k += TL_TPB) s += __ldcg(src + k);
+#pragma unroll 4
+        for (int k = tid; k < ngroups; k += TL_TPB) s += __ldcg(src + k);
         s = warp_sum(s);
         __syncthreads();
         if (lane == 0) sm[r][wid] = s;
@@ -172,7 +201,7 @@ static int launch_generic(tl_chunk* c, int k_lo, int k_hi, int j_lo, int j_hi, F
         tl_set_error("partials capacity exceeded");
         return TL_ERR_ARG;
     }
-    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
     k_generic<NR, F, Fin><<<grid, TL_TPB, 0, c->stream>>>(c->g, k_lo, k_hi, j_lo, j_hi, rows, f, fin, ra);
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
@@ -807,7 +836,7 @@ int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc)
     const int rows = tile_rows(c, TUNE_W);
     dim3 grid = hot_grid(c, rows);
     TL_TRY(hot_check(c, grid));
-    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
 #define LAUNCH_W(U)                                                                                          \
     if (mc && mc->num_ranks > 1)                                                                             \
         k_cg_calc_w<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],          \
@@ -945,7 +974,7 @@ int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const Mul
     const int rows = tile_rows(c, TUNE_UR);
     dim3 grid = hot_grid(c, rows);
     TL_TRY(hot_check(c, grid));
-    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
 #define LAUNCH_UR(U)                                                                                       \
     if (mc && mc->num_ranks > 1)                                                                           \
         k_cg_calc_ur<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],        \
@@ -1311,7 +1340,7 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc)
         c->p2_alloc = c->p2;
         TL_CUDA(cudaMemsetAsync(c->p2, 0, c->field_elems * sizeof(double), c->stream));
     }
-    RedArgs ra{c->partials, c->partial_cap, c->scal};
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
     const int mask = external_mask(c);
 #define LAUNCH_PW(U)                                                                                          \
     if (mc && mc->num_ranks > 1)                                                                              \
