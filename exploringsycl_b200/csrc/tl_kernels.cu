@@ -10,6 +10,7 @@
 // None of this is GEMM-shaped: the path is HBM-bound (0.22 flop/B), so the design rules are
 // coalesced 128-bit accesses on 128-byte-aligned rows, enough independent loads in flight,
 // and the minimum number of passes over HBM.  Tensor cores / TMEM are not used.
+#include <stdlib.h>
 #include "tl_internal.h"
 
 long g_tl_launches = 0;
@@ -713,8 +714,25 @@ extern "C" int tl_set_tuning(int kernel, int rows, int batch)
     g_batch[kernel] = batch;
     return TL_OK;
 }
+// TL_TUNE="kernel:rows:batch,..." (e.g. "1:16:4,2:16:4") overrides the defaults at first use: experiments only.
+static void tune_from_env()
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char* e = getenv("TL_TUNE");
+    if (!e) return;
+    int k, r, b;
+    while (*e) {
+        if (sscanf(e, "%d:%d:%d", &k, &r, &b) == 3) tl_set_tuning(k, r, b);
+        while (*e && *e != ',') ++e;
+        if (*e == ',') ++e;
+    }
+}
+
 static int tile_rows(const tl_chunk* c, int kernel)
 {
+    tune_from_env();
     if (g_rows[kernel] > 0) return g_rows[kernel];
     if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
     // Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read), but the tile

@@ -313,7 +313,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
         TL_TRY(tl_halo_update(c, k, fields, 1));
         TL_TRY(fetch_cg_coeffs(c, S->iters));
     } else if (use_resident_multi(c, k)) {
-        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w == 2));
+        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w != 0));
         const DevScal* S = c->scal_h;
         error = S->error;
         const bool converged = sqrt(fabs(error)) < o->eps;

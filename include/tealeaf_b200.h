@@ -196,9 +196,10 @@ typedef struct {
     int error_switch;      /* settings.h:32 */
     double eps_lim;        /* settings.h:34 */
     int check_result;      /* settings.h:35: residual + 2norm in solve_finished */
-    int fuse_p_into_w;     /* 0: three kernels per CG iteration as in cg_driver.c; 1 (default): p-update fused into the
-                            * next matvec on one rank, three kernels on several ranks (measured faster there);
-                            * 2: fused on several ranks too (r's halo travels instead of p's). Same results. */
+    int fuse_p_into_w;     /* 0: three kernels per CG iteration as in cg_driver.c (p's halo travels between ranks);
+                            * non-zero (default 1): p-update fused into the next matvec, two kernels per iteration
+                            * (r's halo travels between ranks); also selects the one-pass Chebyshev / PPCG kernels.
+                            * Results are bit-identical either way. */
     int batch;             /* iterations enqueued between convergence polls (0 = default) */
 } tl_solve_opts;
 
