@@ -294,7 +294,8 @@ def main():
             traffic = None
     # the resident CG iteration is cg_calc_pw (fused p-update + matvec) + cg_calc_ur: the dominant kernel
     # is whichever of the two takes longer per launch
-    fused_run = bool(s.fuse_p_into_w)
+    lr_nb = app.decomposition["x_chunks"] > 1
+    fused_run = s.fuse_p_into_w == 2 or (s.fuse_p_into_w == 1 and not lr_nb)
     dom_name = "cg_calc_pw" if (fused_run and kern["cg_calc_pw"]["ms"] >= kern["cg_calc_ur"]["ms"]) \
         else "cg_calc_ur"
     dom = kern[dom_name]
@@ -337,7 +338,7 @@ def main():
                            "l2": "inputs larger than L2: 7 live fields x %.0f MB per GPU" % (ch.x * ch.y * 8 / 1e6),
                            "bytes_per_cell_iter": BYTES_PER_CELL_ITER,
                            "iteration": "cg_calc_pw + cg_calc_ur (96 B/cell moved)"
-                           if s.fuse_p_into_w
+                           if fused_run
                            else "cg_calc_w + cg_calc_ur + cg_calc_p (104 B/cell moved)"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu, "wall_s": wall, "summary": summary}

@@ -77,7 +77,7 @@ class Settings:  # settings.h:64-123 with the defaults of settings.h:15-45
     fields_to_exchange: List[bool] = dc_field(default_factory=lambda: [False] * NUM_FIELDS)
     # extensions of this backend (not in the reference)
     batch: int = 0
-    fuse_p_into_w: int = 1  # 0: reference kernel sequence; 1: fused kernels (bit-identical), see tl_solve_opts
+    fuse_p_into_w: int = 1  # 0: reference kernel sequence; 1: auto; 2: always fused (bit-identical), see tl_solve_opts
 
     def reset_fields_to_exchange(self):  # settings.c:64-70
         self.fields_to_exchange = [False] * NUM_FIELDS

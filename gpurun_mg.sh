@@ -1,10 +1,9 @@
 cd /root/repo
-for tune in "1:8:4,2:8:4" "1:16:4,2:16:4" "1:32:4,2:32:4" "1:16:2,2:16:4"; do
-for fused in 1 2; do
-TL_TUNE=$tune TL_BENCH_FUSED=$fused timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 1 --warmup 1 --no-e2e --max-iters 3000 2>gpurun_out/b.err | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read())
-print('N=2 tune=$tune fused=$fused value %.4e ms/iter %.4f' % (d['value'], d['ms_per_step']/ 3000))
-" || tail -5 gpurun_out/b.err
-done
+for fused in 0 1; do
+TL_BENCH_FUSED=$fused timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 1 --warmup 1 --no-e2e 2>gpurun_out/b.err | tail -1 > gpurun_out/n8_fused$fused.json
+python -c "
+import json
+d=json.loads(open('gpurun_out/n8_fused$fused.json').read())
+print('N=8 fused=$fused value %.4e ms/step %.1f iters %s' % (d['value'], d['ms_per_step'], d['config']['cg_iterations_per_step']))
+" || tail -3 gpurun_out/b.err
 done

@@ -108,11 +108,11 @@ def test_halo_exchange_bit_exact(world, grid):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("deck,solver,fused", [("tea_250_cg.in", O.CG, 1), ("tea_250_cg.in", O.CG, 0),
+@pytest.mark.parametrize("deck,solver,fused", [("tea_250_cg.in", O.CG, 2), ("tea_250_cg.in", O.CG, 0),
                                                ("tea_250_cheby.in", O.CHEBY, 1),
                                                ("tea_250_ppcg.in", O.PPCG, 1)])
 def test_decomposed_deck_matches_oracle(world, deck, solver, fused):
-    """fused=1: two-kernel iteration, r's halo travels; fused=0: three kernels, p's halo travels."""
+    """fused=2: two-kernel iteration, r's halo travels; fused=0: three kernels, p's halo travels; 1: auto."""
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
     res = launch(deck_worker, world, (deck, {"end_step": 2, "fuse_p_into_w": fused}))
@@ -134,7 +134,7 @@ def test_decomposed_deck_matches_oracle(world, deck, solver, fused):
 def test_fused_and_three_kernel_multi_rank_loops_are_bit_identical(world):
     if ngpus() < world:
         pytest.skip("needs %d GPUs" % world)
-    a = launch(deck_worker, world, ("tea_250_cg.in", {"end_step": 2, "fuse_p_into_w": 1}))
+    a = launch(deck_worker, world, ("tea_250_cg.in", {"end_step": 2, "fuse_p_into_w": 2}))
     b = launch(deck_worker, world, ("tea_250_cg.in", {"end_step": 2, "fuse_p_into_w": 0}))
     for (ra, sa, ha), (rb, sb, hb) in zip(a, b):
         assert sa == sb
