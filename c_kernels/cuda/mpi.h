@@ -1,9 +1,31 @@
 /*
  * mpi.h shim -- TeaLeaf/comms.h:6 includes <mpi.h> and drivers/remote_halo_driver.c:17 declares an
  * array of MPI_Request; nothing else of MPI is used outside comms.c.  With this backend the ranks of
- * one NVSwitch node talk through comms_b200.cpp (shared memory + NVLink peer stores), so the type is
- * all that is needed.  Build WITHOUT -DNO_MPI (that flag compiles the halo exchange out,
- * remote_halo_driver.c:14,128).
+ * one NVSwitch node talk through comms_b200.cpp (shared memory + NVLink peer stores).
+ *
+ * Build WITHOUT -DNO_MPI (that flag compiles the halo exchange out, remote_halo_driver.c:14,128).
+ * The reference Makefile lists comms.o among the prerequisites of `tealeaf` before this directory's
+ * fragment is read, so comms.c still gets compiled: the inline stubs below let it compile; the
+ * fragment then drops comms.o from the link line (comms_b200.o provides the nine functions).
  */
 #pragma once
 typedef int MPI_Request;
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+typedef int MPI_Status;
+#define MPI_COMM_WORLD 0
+#define MPI_DOUBLE 0
+#define MPI_SUM 0
+#define MPI_MIN 1
+#define MPI_STATUSES_IGNORE ((MPI_Status*)0)
+static inline int MPI_Init(int*, char***) { return 0; }
+static inline int MPI_Finalize() { return 0; }
+static inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = 0; return 0; }
+static inline int MPI_Comm_size(MPI_Comm, int* s) { *s = 1; return 0; }
+static inline int MPI_Isend(const void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Request*) { return 0; }
+static inline int MPI_Irecv(void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Request*) { return 0; }
+static inline int MPI_Waitall(int, MPI_Request*, MPI_Status*) { return 0; }
+static inline int MPI_Allreduce(const void*, void*, int, MPI_Datatype, MPI_Op, MPI_Comm) { return 0; }
+static inline int MPI_Barrier(MPI_Comm) { return 0; }
+static inline int MPI_Abort(MPI_Comm, int) { return 0; }
