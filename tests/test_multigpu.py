@@ -140,3 +140,33 @@ def test_fused_and_three_kernel_multi_rank_loops_are_bit_identical(world):
         assert sa == sb
         assert [h["iters_a"] for h in ha] == [h["iters_a"] for h in hb]
         assert [h["error"] for h in ha] == [h["error"] for h in hb]
+
+
+@pytest.mark.parametrize("binary", ["tealeaf_cuda", "tealeaf_cuda_resident"])
+def test_reference_host_on_two_ranks(binary, tmp_path):
+    """The unmodified reference host, one process per GPU (launched with RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_PORT in the environment), with comms_b200.cpp in place of the MPI comms.c: decomposed CG deck
+    vs the oracle's 2-chunk run.  tealeaf_cuda = plugin path (host buffers through the mailboxes),
+    tealeaf_cuda_resident = DIFFUSE_OVERLOAD (device-resident loop, NVLink peer stores)."""
+    import re
+    import shutil
+    import subprocess
+    import sys
+    from tl_testutil import GOLDEN, ROOT
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = os.path.join(ROOT, "oracle", "_ref", binary)
+    if not os.path.exists(exe):
+        pytest.skip("%s not built" % binary)
+    shutil.copy(os.path.join(DECKS, "tea_250_cg.in"), tmp_path / "tea.in")
+    shutil.copy(os.path.join(GOLDEN, "tea_problems.txt"), tmp_path / "tea.problems")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--no-python", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), exe]
+    r = subprocess.run(cmd, cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PASSED" in r.stdout
+    cg = [int(v) for v in re.findall(r"(?m)^CG:\s+(\d+) iterations", r.stdout)]
+    actual = float(re.search(r"Actual\s+(\S+)", r.stdout).group(1))
+    ores = O.run_deck(O.make_deck(250, num_chunks=2))
+    assert len(cg) == 10 and all(abs(a - b) <= 1 for a, b in zip(cg, ores["iters_a"])), (cg, ores["iters_a"])
+    assert rel(actual, ores["temp"]) < 1e-10
