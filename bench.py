@@ -111,7 +111,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    nx, ny = mesh_for(args.gpus)
+    nx, ny = args.mesh if args.mesh else mesh_for(args.gpus)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cap = args.ref_iters

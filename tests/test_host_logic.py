@@ -72,3 +72,51 @@ def test_checking_value():
     assert get_checking_value(os.path.join(GOLDEN, "tea_problems.txt"), s) == 9.5462351582214282e+01
     s.end_step = 3
     assert get_checking_value(os.path.join(GOLDEN, "tea_problems.txt"), s) is None
+
+
+QUIRK_DECKS = {
+    "quirks": "*tea\nstate 1 density=1.0 energy=2.0\nstate 2 density=0.5 energy=3.5 geometry=rectangle xmin=1.0 xmax=2.0 "
+              "ymin=0.5 ymax=3.0\n  x_cells=32\ny_cells=48\nxmin=-1.0\nxmax=7.0\nymax=3.0\nepslim=1e-4\neps 1e-12\n"
+              "use_chebyshev\nerrswitch\npresteps=12\nppcg_inner_steps=7\ncoefficient_inverse_density\n"
+              "initial_timestep=0.01\nend_step=3\nmax_iters=777\nsummary_frequency=2\ntl_something 5\nprofiler_on\n"
+              "*endtea\n",
+    "circle": "*tea\nstate 1 density=100.0 energy=0.0001\nstate 2 density=0.1 energy=25.0 geometry=circular xmin=5.0 "
+              "xmax=0.0 ymin=5.0 ymax=0.0 radius=2.5\nstate 3 density=7 energy=1 geometry=point xmin=1.0 xmax=0 ymin=2.0 "
+              "ymax=0\nx_cells=20\ny_cells=30\nxmax=10.0\nymax=10.0\nend_step=1\nuse_jacobi\n*endtea\n",
+}
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(O.REF_BIN), "print_config")),
+                    reason="oracle/_ref/print_config not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("deck", ["tea_250_cg.in", "tea_250_cheby.in", "tea_250_ppcg.in", "tea_10_jacobi.in",
+                                  "tea_4000_cg.in", "quirks", "circle"])
+def test_read_config_matches_the_reference_parser(deck, tmp_path):
+    """exploringsycl_b200.read_config vs the reference's own parse_config.c (compiled in place into
+    oracle/_ref/print_config): every Settings field and every State, bit for bit."""
+    import subprocess
+    from exploringsycl_b200 import read_config
+    path = tmp_path / "tea.in"
+    if deck in QUIRK_DECKS:
+        path.write_text(QUIRK_DECKS[deck])
+    else:
+        path.write_text(open(os.path.join(DECKS, deck)).read())
+    out = subprocess.run([os.path.join(os.path.dirname(O.REF_BIN), "print_config")], cwd=tmp_path,
+                         capture_output=True, text=True, timeout=60).stdout
+    ref, ref_states = {}, []
+    for line in out.splitlines():
+        tok = line.split()
+        if tok[0] == "state":
+            ref_states.append([float(t) for t in tok[2:]])
+        else:
+            ref[tok[0]] = float(tok[1])
+    s, st = read_config(str(path))
+    for key in ("grid_x_cells", "grid_y_cells", "end_step", "max_iters", "presteps", "ppcg_inner_steps",
+                "summary_frequency", "halo_depth", "num_states", "solver", "coefficient", "dt_init", "eps",
+                "eps_lim", "end_time", "grid_x_min", "grid_y_min", "grid_x_max", "grid_y_max", "dx", "dy"):
+        assert float(getattr(s, key)) == ref[key], key
+    assert float(s.error_switch) == ref["error_switch"] and float(s.check_result) == ref["check_result"]
+    assert len(st) == len(ref_states)
+    for n, (a, b) in enumerate(zip(st, ref_states)):
+        mine = [a.density, a.energy] if n == 0 else [a.density, a.energy, float(a.geometry), a.x_min, a.y_min,
+                                                      a.x_max, a.y_max]
+        assert mine == b, (n, mine, b)
