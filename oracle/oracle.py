@@ -68,6 +68,7 @@ def lib():
         pd = C.POINTER(C.c_double)
         sig = {
             "orc_tree_sum": ([p, C.c_long], d),
+            "orc_set_sum_mode": ([i], None),
             "orc_set_chunk_data": ([i, i, i, d, d, d, d, p, p, p, p, p], None),
             "orc_set_chunk_initial_state": ([i, i, d, d, p, p], None),
             "orc_set_chunk_state": ([i, i, i, i, d, d, d, d, d, d, d, p, p, p, p, p, p, p], None),
@@ -139,7 +140,16 @@ def make_deck(x_cells, y_cells=None, solver=CG, end_step=10, num_chunks=1, max_i
     return d
 
 
-def run_deck(deck, want_fields=False):
+def run_deck(deck, want_fields=False, gpu_sum_order=False):
+    """gpu_sum_order=True: reductions replay the CUDA backend's tree (bit-for-bit comparable solves)."""
+    lib().orc_set_sum_mode(1 if gpu_sum_order else 0)
+    try:
+        return _run_deck(deck, want_fields)
+    finally:
+        lib().orc_set_sum_mode(0)
+
+
+def _run_deck(deck, want_fields=False):
     res = OrcResult()
     u = en = None
     pu = pe = None

@@ -76,11 +76,100 @@ static double* partials(long ng)
     return g_partials;
 }
 
+/* ------------------------------------------------------------------------- */
+/* Optional summation order: replay of the CUDA backend's (deterministic) reduction tree, so that a
+ * whole solve can be compared with the GPU bit for bit (iteration counts included).  Mode 0 (default)
+ * is the reference's order above; mode 1 replays exploringsycl_b200/csrc/tl_kernels.cu:
+ *   thread: sequential over its rows (and its 1 or 2 columns) -> warp xor-butterfly -> 4 warps
+ *   (s0+s1)+(s2+s3) = tile partial; 64 tiles per group (lanes of two warps, s0+s1); groups summed
+ *   by 128 threads striding, butterfly, (s0+s1)+(s2+s3).                                         */
+static int g_sum_mode = 0;
+void orc_set_sum_mode(int mode) { g_sum_mode = mode; }
+
+static double butterfly32(double* v) /* lane 0's value after xor-butterfly 1,2,4,8,16 */
+{
+    for (int o = 1; o < 32; o <<= 1)
+        for (int l = 0; l < 32; l += 2 * o) v[l] = v[l] + v[l + o];
+    return v[0];
+}
+static double block128(double* t) /* 128 per-thread values -> CTA value */
+{
+    double w0 = butterfly32(t), w1 = butterfly32(t + 32), w2 = butterfly32(t + 64), w3 = butterfly32(t + 96);
+    return (w0 + w1) + (w2 + w3);
+}
+enum { SUM_GENERIC = 0, SUM_HOT_W = 1, SUM_HOT_UR = 2 };
+static int gpu_tile_rows(int kind, int nx, int ny)
+{
+    if (kind != SUM_HOT_W) return 8;
+    int colb = (nx + 255) / 256;
+    int rowblocks = (8 * 148) / colb;
+    if (rowblocks < 1) rowblocks = 1;
+    int rows = (ny + rowblocks - 1) / rowblocks;
+    if (rows < 8) rows = 8;
+    if (rows > 128) rows = 128;
+    return rows;
+}
+static double gpu_order_sum(const double* val, int x, int y, int hd, int kind)
+{
+    const int nx = x - 2 * hd, ny = y - 2 * hd;
+    const int cpt = (kind == SUM_GENERIC) ? 1 : 2, tile_cols = 128 * cpt;
+    const int rows = gpu_tile_rows(kind, nx, ny);
+    const int gx = (nx + tile_cols - 1) / tile_cols, gy = (ny + rows - 1) / rows;
+    const long ntiles = (long)gx * gy;
+    double* part = (double*)malloc(sizeof(double) * (size_t)ntiles);
+#pragma omp parallel for schedule(static)
+    for (long tile = 0; tile < ntiles; ++tile) {
+        const int bx = (int)(tile % gx), by = (int)(tile / gx);
+        const int j0 = hd + by * rows, j1 = (j0 + rows < y - hd) ? j0 + rows : y - hd;
+        double t[128];
+        for (int tx = 0; tx < 128; ++tx) {
+            double acc = 0.0;
+            const int kk = hd + cpt * (bx * 128 + tx);
+            for (int jj = j0; jj < j1; ++jj)
+                for (int c = 0; c < cpt; ++c)
+                    if (kk + c < x - hd) acc += val[(long)(kk + c) + (long)jj * x];
+            t[tx] = acc;
+        }
+        part[tile] = block128(t);
+    }
+    const long ngroups = (ntiles + 63) / 64;
+    double* gp = (double*)malloc(sizeof(double) * (size_t)ngroups);
+    for (long g = 0; g < ngroups; ++g) {
+        double t[64];
+        for (int l = 0; l < 64; ++l) t[l] = (g * 64 + l < ntiles) ? part[g * 64 + l] : 0.0;
+        double w0 = butterfly32(t), w1 = butterfly32(t + 32);
+        gp[g] = w0 + w1;
+    }
+    double t[128];
+    for (int tid = 0; tid < 128; ++tid) {
+        double s = 0.0;
+        for (long k = tid; k < ngroups; k += 128) s += gp[k];
+        t[tid] = s;
+    }
+    const double total = block128(t);
+    free(part);
+    free(gp);
+    return total;
+}
+
 /* Generic "nd64" reduction kernel shape: range ceil(x*y/64)*64, one work-item per
  * flat index, interior test inside, value 0 elsewhere (e.g. cg.cpp:96-127). */
-#define ND64_REDUCE(RESULT, CELL_EXPR)                                              \
+#define ND64_REDUCE(RESULT, CELL_EXPR) ND64_REDUCE_K(RESULT, CELL_EXPR, SUM_GENERIC)
+#define ND64_REDUCE_K(RESULT, CELL_EXPR, KIND)                                      \
     do {                                                                            \
         const long n_ = (long)x * y;                                                \
+        if (g_sum_mode == 1) {                                                      \
+            double* val_ = (double*)calloc((size_t)n_, sizeof(double));             \
+            _Pragma("omp parallel for schedule(static)")                            \
+            for (int jj = hd; jj < y - hd; ++jj)                                    \
+                for (int kk = hd; kk < x - hd; ++kk) {                              \
+                    const long index = (long)kk + (long)jj * x;                     \
+                    val_[index] = (CELL_EXPR);                                      \
+                }                                                                   \
+            (RESULT) = gpu_order_sum(val_, x, y, hd, KIND);                         \
+            free(val_);                                                             \
+            break;                                                                  \
+        }                                                                           \
         const long ng_ = (n_ + 63) / 64;                                            \
         double* part_ = partials(ng_);                                              \
         _Pragma("omp parallel for schedule(static)")                                \
@@ -278,7 +367,7 @@ void orc_cg_calc_w(int x, int y, int hd, const double* p, const double* kx, cons
                    double* w, double* pw)
 {
     double s;
-    ND64_REDUCE(s, (w[index] = SMVP(p, index), w[index] * p[index]));
+    ND64_REDUCE_K(s, (w[index] = SMVP(p, index), w[index] * p[index]), SUM_HOT_W);
     *pw += s;
 }
 
@@ -287,7 +376,7 @@ void orc_cg_calc_ur(int x, int y, int hd, double alpha, const double* p, const d
                     double* u, double* r, double* rrn)
 {
     double s;
-    ND64_REDUCE(s, (u[index] += alpha * p[index], r[index] -= alpha * w[index], r[index] * r[index]));
+    ND64_REDUCE_K(s, (u[index] += alpha * p[index], r[index] -= alpha * w[index], r[index] * r[index]), SUM_HOT_UR);
     *rrn = s;
 }
 

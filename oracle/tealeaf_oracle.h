@@ -44,6 +44,9 @@ enum { ORC_GEOM_RECT = 0, ORC_GEOM_CIRC = 1, ORC_GEOM_POINT = 2 };
 
 /* ---- reduction (sycl_shared.hpp:35-79) ---- */
 double orc_tree_sum(const double* v, long n);
+/* 0 (default): the reference's summation order; 1: replay of the CUDA backend's deterministic reduction
+ * tree (tile -> 64-tile group -> total), which makes whole solves comparable with the GPU bit for bit. */
+void orc_set_sum_mode(int mode);
 
 /* ---- kernels: dense row-major x*y arrays, i = kk + jj*x ---- */
 void orc_set_chunk_data(int x, int y, int hd, double x_min, double y_min, double dx, double dy,

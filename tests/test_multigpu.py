@@ -170,3 +170,18 @@ def test_reference_host_on_two_ranks(binary, tmp_path):
     ores = O.run_deck(O.make_deck(250, num_chunks=2))
     assert len(cg) == 10 and all(abs(a - b) <= 1 for a, b in zip(cg, ores["iters_a"])), (cg, ores["iters_a"])
     assert rel(actual, ores["temp"]) < 1e-10
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("fused", [2, 0])
+def test_decomposed_cg_is_bit_identical_to_the_oracle_n_chunk_run(world, fused):
+    """With the oracle replaying the GPU summation tree per chunk and adding the chunk sums in rank order
+    (exactly what the NVLink slot reduction does), a decomposed solve matches in every bit."""
+    if ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    res = launch(deck_worker, world, ("tea_250_cg.in", {"end_step": 3, "fuse_p_into_w": fused}))
+    ores = O.run_deck(O.make_deck(250, end_step=3, num_chunks=world), gpu_sum_order=True)
+    for rank, summary, hist in res:
+        assert [h["iters_a"] for h in hist] == ores["iters_a"]
+        assert [h["error"] for h in hist] == ores["error"]
+        assert [summary[k] for k in ("vol", "mass", "ie", "temp")] == [ores[k] for k in ("vol", "mass", "ie", "temp")]
