@@ -10,13 +10,16 @@ eps = 1e-15 (cg_driver.c), residual check, finalise, energy halo -- on the stand
 
   N = 1 : 4000 x 4000 mesh  (BASELINE.json configs[1], tea_bm_5)
   N > 1 : weak scaling at 16 M cells per GPU:
-          4000x8000 @2, 8000x8000 @4, 8000x16000 @8, decomposed by the reference's decompose_field.
+          4000x8000 @2, 8000x8000 @4, 8000x16000 @8, decomposed by the reference's decompose_field; halos and the
+          two per-iteration scalars move GPU to GPU over NVLink peer memory inside the solver kernels (no NCCL on
+          the data path; torch.distributed/NCCL only provides the barrier and the max-over-ranks of the timing).
 
 metric  = CG cell-iterations per second = x_cells * y_cells * (CG iterations executed) / time
 value   = whole job, state resident in HBM, timed with CUDA events on the solver stream, max over ranks
 e2e     = same metric through tl_timestep_host(): density + energy images uploaded from pinned host
           memory and energy + summary read back inside the timed region, every step
-roofline= dominant kernel (cg_calc_ur, 48 B/cell) timed live with CUDA events vs MEASURED_PEAKS.json
+roofline= dominant kernel of the iteration (cg_calc_pw or cg_calc_ur, 48 B/cell each) timed live with CUDA events on
+          the launching stream vs MEASURED_PEAKS.json; traffic = ncu DRAM bytes per launch (profiles/traffic.json)
 cpu_baseline / --impl reference = the CPU oracle (C + OpenMP restatement of the reference kernels and
           drivers; the reference's own SYCL kernels cannot be built here) on the box's host cores.
 """
