@@ -120,3 +120,31 @@ def test_read_config_matches_the_reference_parser(deck, tmp_path):
         mine = [a.density, a.energy] if n == 0 else [a.density, a.energy, float(a.geometry), a.x_min, a.y_min,
                                                       a.x_max, a.y_max]
         assert mine == b, (n, mine, b)
+
+
+def test_decomposition_invariants_property():
+    """Hypothesis: for any mesh and rank count the chunks tile the mesh exactly once, neighbours are mutual,
+    and the library agrees with the oracle's restatement of initialise.c:34-134."""
+    from hypothesis import given, settings as hsettings, strategies as st
+    from exploringsycl_b200 import decompose_field
+
+    @hsettings(max_examples=60, deadline=None)
+    @given(st.integers(8, 3000), st.integers(8, 3000), st.sampled_from([1, 2, 3, 4, 5, 6, 7, 8]))
+    def check(gx, gy, n):
+        ds = [decompose_field(gx, gy, n, c) for c in range(n)]
+        cover = np.zeros((gy, gx), dtype=np.int32)
+        for d in ds:
+            cover[d["bottom"]:d["bottom"] + d["ny"], d["left"]:d["left"] + d["nx"]] += 1
+        assert cover.min() == 1 and cover.max() == 1
+        opp = {0: 1, 1: 0, 2: 3, 3: 2}
+        for c, d in enumerate(ds):
+            for face, nb in enumerate(d["neighbours"]):
+                if nb != -1:
+                    assert ds[nb]["neighbours"][opp[face]] == c
+                    if face in (0, 1):  # left/right neighbours share the row extent
+                        assert ds[nb]["bottom"] == d["bottom"] and ds[nb]["ny"] == d["ny"]
+                    else:
+                        assert ds[nb]["left"] == d["left"] and ds[nb]["nx"] == d["nx"]
+        assert all(d["x_chunks"] * d["y_chunks"] == n for d in ds)
+
+    check()
