@@ -210,7 +210,9 @@ def main():
     L = lib()
     comms = None
     if world > 1:
-        session = "bench_%s" % os.environ.get("MASTER_PORT", "0")
+        # all workers of one torchrun launch share the agent as parent: a per-launch name, so a segment left
+        # behind by a crashed earlier run on the same port can never be picked up
+        session = "bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
         comms = Comms(session, rank, world, device=local_rank)
     s, states = deck_settings(nx, ny, args.max_iters)
     s.solver = {"jacobi": 0, "cg": 1, "cheby": 2, "ppcg": 3}[args.solver]

@@ -7,6 +7,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 #include <vector>
 #include "comms.h"
 #include "chunk.h"
@@ -35,8 +36,9 @@ void initialise_comms(int argc, char** argv)
     g_local = env_int("LOCAL_RANK", g_rank);
     if (g_size > 1) {
         const char* port = getenv("MASTER_PORT");
-        char session[64];
-        snprintf(session, sizeof(session), "tealeaf_%s", port ? port : "0");
+        char session[96];
+        // per-launch name: every rank of one launch has the launcher as parent process
+        snprintf(session, sizeof(session), "tealeaf_%s_%d", port ? port : "0", (int)getppid());
         if (tl_comms_create(&g_comms, session, g_rank, g_size, g_local, 0) != TL_OK) {
             fprintf(stderr, "initialise_comms: %s\n", tl_last_error());
             exit(1);
