@@ -30,6 +30,7 @@ static void fields_reset(int* f) { memset(f, 0, sizeof(int) * TL_NUM_EXCHANGE_FI
 extern "C" int tl_halo_update(tl_chunk* c, tl_comms* k, const int fields_to_exchange[6], int depth)
 {
     TL_CHECK_ARG(c && fields_to_exchange, "null argument");
+    TL_CHECK_ARG(depth >= 1 && depth <= c->g.hd, "depth must be between 1 and halo_depth");
     TL_CUDA(cudaSetDevice(c->device));
     bool any = false;
     for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i) any |= (fields_to_exchange[i] != 0);
