@@ -171,10 +171,13 @@ extern "C" int tl_comms_destroy(tl_comms* k)
                 if (k->peer_pfield_base[r]) cudaIpcCloseMemHandle(k->peer_pfield_base[r]);
             }
     }
+    // Unlink the name BEFORE the last barrier: once any rank has left this function the name no longer
+    // resolves to this (still mapped) segment, so an immediate re-create under the same name cannot attach
+    // a rank to the dying segment.
+    if (k->rank == 0) shm_unlink(k->name);
     tl_comms_barrier(k);
     if (k->arena) cudaFree(k->arena);
     munmap(k->hdr, k->shm_bytes);
-    if (k->rank == 0) shm_unlink(k->name);
     delete k;
     return TL_OK;
 }

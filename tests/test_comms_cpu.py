@@ -211,3 +211,37 @@ def test_cg_over_product_comms_matches_oracle_n_chunk_run(world):
         assert r["sum_ok"] and r["min_ok"] and r["ring_ok"]
         assert r["iters"] == ref["iters_a"]
         assert r["summary"] == [ref["vol"], ref["mass"], ref["ie"], ref["temp"]]  # bit-exact
+
+
+def _err_worker(rank, world, session, out):
+    from exploringsycl_b200 import Comms, TeaLeafError
+    res = {}
+    for rep in range(2):  # the same session name can be created again after a clean teardown
+        comms = Comms(session, rank, world, host_only=True)
+        other = 1 - rank
+        send = np.full(5 + rank, float(rank))  # rank 0 sends 5 doubles, rank 1 sends 6
+        recv = np.zeros(5 + rank)               # ... and each expects its OWN length: mismatch
+        try:
+            comms.send_recv_message(send, recv, other, 0, 0)
+            res["rep%d" % rep] = "no error"
+        except TeaLeafError as e:
+            res["rep%d" % rep] = str(e)
+        comms.barrier()
+        comms.finalise()
+    out.put((rank, res))
+
+
+def test_message_length_mismatch_is_reported_and_session_is_reusable():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    session = "pytest_err_%d" % os.getpid()
+    procs = [ctx.Process(target=_err_worker, args=(r, 2, session, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(out.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in (0, 1):
+        for rep in (0, 1):
+            assert "message length mismatch" in res[rank]["rep%d" % rep]
