@@ -18,10 +18,18 @@ metric  = CG cell-iterations per second = x_cells * y_cells * (CG iterations exe
 value   = whole job, state resident in HBM, timed with CUDA events on the solver stream, max over ranks
 e2e     = same metric through tl_timestep_host(): density + energy images uploaded from pinned host
           memory and energy + summary read back inside the timed region, every step
+parity  = BEFORE anything is timed: a 250x250 deck decomposed over the N ranks (three-kernel and fused resident
+          loops) must equal the CPU oracle's N-chunk run in every bit (iteration counts, per-step residuals, the four
+          field-summary sums), and 60 back-to-back halo exchanges verified cell by cell on the device; the run
+          FAILS otherwise.  (The oracle is the checker here, never the thing measured.)
 roofline= dominant kernel of the iteration (cg_calc_pw or cg_calc_ur, 48 B/cell each) timed live with CUDA events on
-          the launching stream vs MEASURED_PEAKS.json; traffic = ncu DRAM bytes per launch (profiles/traffic.json)
+          the launching stream vs MEASURED_PEAKS.json; traffic = DRAM bytes per launch of that kernel from the
+          committed ncu capture (profiles/traffic.json; null when the capture does not cover the kernel)
+extra   = (N > 1) the other named configs of BASELINE.json, device-timed the same way with the iteration count capped:
+          strong scaling of 4000x4000 over the N GPUs; at N = 8 also CG 16000^2 and 32000^2 and Chebyshev / PPCG 8000^2
 cpu_baseline / --impl reference = the CPU oracle (C + OpenMP restatement of the reference kernels and
-          drivers; the reference's own SYCL kernels cannot be built here) on the box's host cores.
+          drivers; the reference's own SYCL kernels cannot be built here) on the box's host cores: solver time only
+          (the oracle's wall_solve_s), CG capped at >= 100 iterations per step whatever the mesh.
 """
 import argparse
 import ctypes as C
@@ -39,6 +47,8 @@ sys.path.insert(0, ROOT)
 BYTES_PER_CELL_ITER = 104  # calc_w 32 + calc_ur 48 + calc_p 24
 KERNELS = ((0, "cg_calc_w", 32), (1, "cg_calc_ur", 48), (2, "cg_calc_p", 24), (3, "cg_calc_pw", 48))
 WEAK_MESH = {1: (4000, 4000), 2: (4000, 8000), 4: (8000, 8000), 8: (8000, 16000)}
+CPU_MIN_ITERS = 100   # floor of the CPU sample per step, whatever the mesh
+CPU_BUDGET_S = 180.0  # target wall time of a whole --impl reference run
 
 
 def mesh_for(n_gpus):
@@ -97,14 +107,24 @@ def deck_settings(nx, ny, max_iters=10000):
     return s, states
 
 
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (C + OpenMP), solver time only
+# ------------------------------------------------------------------------------------------------
 def cpu_port_run(nx, ny, iters_cap, steps):
-    """Times the CPU oracle (C + OpenMP) on `steps` timesteps capped at iters_cap CG iterations."""
+    """`steps` timesteps of the standard deck from t = 0 with CG capped at iters_cap iterations each.
+    Returns (cell_iters, solver seconds): the oracle times cg_driver only (wall_solve_s), so deck
+    allocation and set-up -- which the GPU arm does not time either -- stay outside."""
     from oracle import oracle as O
     d = O.make_deck(nx, ny, end_step=steps, max_iters=iters_cap)
-    t0 = time.perf_counter()
     r = O.run_deck(d)
-    wall = time.perf_counter() - t0
-    return r, wall
+    return r["cell_iters"], r["wall_solve_s"]
+
+
+def cpu_iters_cap(nx, ny, seconds_per_step, hard_max=2000):
+    """Iterations per step that fit `seconds_per_step` on this host, never below CPU_MIN_ITERS."""
+    ci, w = cpu_port_run(nx, ny, 8, 1)  # probe (also the first-touch / thread-pool warm-up)
+    per_iter = max(w / max(ci / (nx * ny), 1.0), 1e-6)
+    return max(CPU_MIN_ITERS, min(hard_max, int(seconds_per_step / per_iter))), per_iter
 
 
 def run_reference(args):
@@ -117,31 +137,24 @@ def run_reference(args):
     nx, ny = args.mesh if args.mesh else mesh_for(args.gpus)
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    cap = args.ref_iters
-    # one untimed probe step sizes the sample so the whole run stays within a few minutes
-    r, wall = cpu_port_run(nx, ny, 4, 1)
-    per_iter = max(wall / 6.0, 1e-4)
-    budget = 150.0 / max(args.steps + args.warmup, 1)
-    cap = max(4, min(cap, int(budget / per_iter)))
-    for _ in range(args.warmup):
-        cpu_port_run(nx, ny, cap, 1)
-    t0 = time.perf_counter()
-    cell_iters = 0
-    for _ in range(args.steps):
-        r, _w = cpu_port_run(nx, ny, cap, 1)
-        cell_iters += r["cell_iters"]
-    wall = time.perf_counter() - t0
-    value = cell_iters / wall
-    sample = "%dx%d mesh, %d timestep(s) of the standard deck from t=0, CG capped at %d iterations each" % (
-        nx, ny, args.steps, cap)
+    threads = int(os.environ["OMP_NUM_THREADS"])
+    cap, per_iter = cpu_iters_cap(nx, ny, CPU_BUDGET_S / max(args.steps + args.warmup, 1))
+    if args.ref_iters:
+        cap = max(CPU_MIN_ITERS if nx * ny > 100 * 100 else 1, min(cap, args.ref_iters))
+    if args.warmup:
+        cpu_port_run(nx, ny, cap, args.warmup)
+    cell_iters, solve_s = cpu_port_run(nx, ny, cap, args.steps)
+    value = cell_iters / solve_s
+    sample = ("%dx%d mesh, %d timestep(s) of the standard deck from t=0, CG capped at %d iterations each "
+              "(floor %d), solver time only, %d OpenMP threads" % (nx, ny, args.steps, cap, CPU_MIN_ITERS, threads))
     line = {"impl": "reference", "metric": "CG cell-iterations/s", "value": value, "unit": "cell-iter/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * solve_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "TeaLeaf CG fp64 %dx%d (tea_bm_5 deck geometry), CPU bounded sample" % (nx, ny),
-                       "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "cell-iter/s", "cores": cores, "kind": "port",
-                             "sample": sample},
+                       "sample": sample, "iters_cap": cap},
+            "cpu_baseline": {"value": value, "unit": "cell-iter/s", "cores": threads, "kind": "port",
+                             "sample": sample, "iters_cap": cap, "host_cpus": cores},
             "e2e": {"value": value, "unit": "cell-iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gb_per_s_algorithmic": value * BYTES_PER_CELL_ITER / 1e9}
     print(json.dumps(line))
@@ -154,10 +167,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--ref-iters", type=int, default=200)
+    ap.add_argument("--ref-iters", type=int, default=0, help="upper bound of the CPU sample (0 = sized by time)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other named configs at N > 1")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--mesh", type=int, nargs=2, default=None)
     ap.add_argument("--solver", default="cg", choices=["cg", "cheby", "ppcg", "jacobi"],
                     help="non-default solvers are reported under their own metric name (BASELINE configs[3])")
@@ -177,7 +192,7 @@ def main():
     os.dup2(2, 1)
     import torch
     import torch.distributed as dist
-    from exploringsycl_b200 import Comms, TeaLeaf, lib
+    from exploringsycl_b200 import Comms, TeaLeaf, lib, read_config
     from exploringsycl_b200._lib import TlSolveInfo, check
 
     torch.cuda.set_device(local_rank)
@@ -206,50 +221,76 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    nx, ny = args.mesh if args.mesh else mesh_for(n_gpus)
     L = lib()
-    comms = None
-    if world > 1:
-        # all workers of one torchrun launch share the agent as parent: a per-launch name, so a segment left
-        # behind by a crashed earlier run on the same port can never be picked up
-        session = "bench_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid())
-        comms = Comms(session, rank, world, device=local_rank)
-    s, states = deck_settings(nx, ny, args.max_iters)
-    s.solver = {"jacobi": 0, "cg": 1, "cheby": 2, "ppcg": 3}[args.solver]
-    inner = s.ppcg_inner_steps if args.solver == "ppcg" else 0
+    n_sessions = [0]
 
-    def matvecs(info):  # solver-loop iterations (+ the reduction-free inner steps of PPCG)
-        return info.total_iters + info.iters_b * inner
-    if os.environ.get("TL_BENCH_FUSED") is not None:
-        s.fuse_p_into_w = int(os.environ["TL_BENCH_FUSED"])
-    app = TeaLeaf(s, states, comms, device=local_rank)
-    ch = app.chunk
+    def new_comms():
+        # all workers of one torchrun launch share the agent as parent: a per-launch name, so a segment left
+        # behind by a crashed earlier run on the same port can never be picked up.  One endpoint per chunk.
+        if world == 1:
+            return None
+        n_sessions[0] += 1
+        session = "bench_%s_%d_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid(), n_sessions[0])
+        return Comms(session, rank, world, device=local_rank)
+
+    solver_id = {"jacobi": 0, "cg": 1, "cheby": 2, "ppcg": 3}
+
+    # ---------------- parity: before anything is timed ----------------
+    parity = None
+    if not args.no_parity:
+        parity = parity_leg(L, new_comms, world, rank, local_rank, sum_over_ranks)
+        if not (parity["n_chunk_bit_exact"] and parity["halo_bit_exact"] in (True, None)):
+            raise SystemExit("bench.py: parity against the CPU oracle FAILED: %s" % json.dumps(parity))
+
+    def timed_case(nx, ny, solver, max_iters, steps, warmup, fuse=None, keep=False):
+        """One configuration, state resident in HBM: `steps` timesteps timed with CUDA events, max over ranks."""
+        comms = new_comms()
+        s, states = deck_settings(nx, ny, max_iters)
+        s.solver = solver_id[solver]
+        if fuse is not None:
+            s.fuse_p_into_w = fuse
+        inner = s.ppcg_inner_steps if solver == "ppcg" else 0
+        app = TeaLeaf(s, states, comms, device=local_rank)
+        for tt in range(warmup):
+            app.solve(tt)
+        barrier()
+        l0 = L.tl_kernel_launch_count()
+        check(L.tl_timer_start(app.chunk.handle))
+        iters, per_step = 0, []
+        for tt in range(steps):
+            info = app.solve(warmup + tt)
+            iters += info.total_iters + info.iters_b * inner  # solver-loop iterations (+ PPCG's inner steps)
+            per_step.append(info.iters_a if solver in ("cg", "jacobi") else [info.iters_a, info.iters_b])
+        ms = C.c_double()
+        check(L.tl_timer_stop(app.chunk.handle, C.byref(ms)))
+        barrier()
+        gpu_s = max_over_ranks(ms.value / 1e3)
+        out = {"value": nx * ny * iters / gpu_s, "gpu_s": gpu_s, "iters": iters, "per_step": per_step,
+               "launches": L.tl_kernel_launch_count() - l0, "summary": app.field_summary_driver(),
+               "decomposition": [app.decomposition["x_chunks"], app.decomposition["y_chunks"]]}
+        if keep:
+            out.update(app=app, comms=comms, settings=s)
+        else:
+            app.close()
+            if comms:
+                comms.finalise()
+        return out
+
+    nx, ny = args.mesh if args.mesh else mesh_for(n_gpus)
+    fuse_env = int(os.environ["TL_BENCH_FUSED"]) if os.environ.get("TL_BENCH_FUSED") is not None else None
     cells = nx * ny
 
     # ---------------- value: state resident in HBM ----------------
-    for tt in range(args.warmup):
-        app.solve(tt)
-    barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = L.tl_kernel_launch_count()
-    check(L.tl_timer_start(ch.handle))
     t0 = time.perf_counter()
-    iters = 0
-    per_step = []
-    for tt in range(args.steps):
-        info = app.solve(args.warmup + tt)
-        iters += matvecs(info)
-        per_step.append(info.iters_a if args.solver in ("cg", "jacobi") else [info.iters_a, info.iters_b])
-    ms = C.c_double()
-    check(L.tl_timer_stop(ch.handle, C.byref(ms)))
-    barrier()
+    main_case = timed_case(nx, ny, args.solver, args.max_iters, args.steps, args.warmup, fuse_env, keep=True)
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    launches = L.tl_kernel_launch_count() - l0
-    gpu_s = max_over_ranks(ms.value / 1e3)
-    value = cells * iters / gpu_s
-    summary = app.field_summary_driver()
+    app, comms, s = main_case["app"], main_case["comms"], main_case["settings"]
+    ch = app.chunk
+    value, gpu_s, launches = main_case["value"], main_case["gpu_s"], main_case["launches"]
+    inner = s.ppcg_inner_steps if args.solver == "ppcg" else 0
 
     # ---------------- e2e: host buffers, copies inside the timed region ----------------
     e2e = None
@@ -270,7 +311,7 @@ def main():
         for tt in range(args.steps):
             check(L.tl_timestep_host(ch.handle, comms.handle if comms else None, C.byref(o), s.dt_init, s.dx,
                                      s.dy, hd_p, he_p, C.byref(info), C.byref(summ)))
-            e_iters += matvecs(info)
+            e_iters += info.total_iters + info.iters_b * inner
         barrier()
         e_wall = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": cells * e_iters / e_wall, "unit": "cell-iter/s",
@@ -281,7 +322,7 @@ def main():
         L.tl_host_free_pinned(hd_p)
         L.tl_host_free_pinned(he_p)
 
-    # ---------------- roofline: the hot kernels timed live (rank 0's chunk) ----------------
+    # ---------------- roofline: the hot kernels timed live (this rank's chunk; rank 0 reports) ----------------
     peak, peak_src = measured_peak()
     kern = {}
     chunk_cells = ch.nx * ch.ny
@@ -290,43 +331,64 @@ def main():
         check(L.tl_time_kernel(ch.handle, which, 40, C.byref(kms)))
         kern[name] = {"ms": kms.value, "bytes_per_cell": bpc, "gb_s": chunk_cells * bpc / kms.value / 1e6,
                       "frac": chunk_cells * bpc / kms.value / 1e6 / peak}
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("cg_calc_ur", {}).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    # the resident CG iteration is cg_calc_pw (fused p-update + matvec) + cg_calc_ur: the dominant kernel
-    # is whichever of the two takes longer per launch
-    lr_nb = app.decomposition["x_chunks"] > 1
-    fused_run = s.fuse_p_into_w == 2 or (s.fuse_p_into_w == 1 and not lr_nb)
+    # the resident CG iteration is cg_calc_pw (fused p-update + matvec) + cg_calc_ur, or the three reference kernels:
+    # the dominant kernel is whichever of the loop's kernels takes longest per launch
+    fused_run = bool(L.tl_cg_loop_is_fused(ch.handle, s.fuse_p_into_w))
     dom_name = "cg_calc_pw" if (fused_run and kern["cg_calc_pw"]["ms"] >= kern["cg_calc_ur"]["ms"]) \
         else "cg_calc_ur"
     dom = kern[dom_name]
-    if os.path.exists(tp):
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp) and (nx, ny, n_gpus) == (4000, 4000, 1):
         try:
-            traffic = json.load(open(tp)).get(dom_name, {}).get("dram_bytes_per_launch")
+            ent = json.load(open(tp)).get(dom_name, {})
+            traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["gb_s"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": chunk_cells * dom["bytes_per_cell"], "kernels": kern,
                 "solve_gb_s_104B": value / n_gpus * BYTES_PER_CELL_ITER / 1e9,
                 "solve_frac_104B": value / n_gpus * BYTES_PER_CELL_ITER / 1e9 / peak}
+    decomposition = app.decomposition
+    app.close()
+    if comms:
+        comms.finalise()
+
+    # ---------------- the other named configs (BASELINE.json configs[2..4]), N > 1 ----------------
+    extra = None
+    if world > 1 and not args.no_extra and args.solver == "cg" and not args.mesh:
+        extra = {}
+        cases = [("cg_4000_strong", 4000, 4000, "cg", 1000)]
+        if world == 8:
+            cases += [("cg_16000", 16000, 16000, "cg", 400), ("cg_32000", 32000, 32000, "cg", 200),
+                      ("cheby_8000", 8000, 8000, "cheby", 1000), ("ppcg_8000", 8000, 8000, "ppcg", 300)]
+        for name, ex, ey, solver, cap in cases:
+            try:
+                r = timed_case(ex, ey, solver, cap, 2, 1, fuse_env)
+                it_ms = 1e3 * r["gpu_s"] / max(r["iters"], 1)
+                bpc = {"cg": 104, "cheby": 88, "ppcg": 80}[solver]  # SURVEY.md 8d algorithmic bytes per cell-iteration
+                extra[name] = {"mesh": [ex, ey], "solver": solver, "value": r["value"], "unit": "cell-iter/s",
+                               "max_iters": cap, "steps": 2, "warmup": 1, "iters": r["iters"],
+                               "ms_per_iter": it_ms, "decomposition": r["decomposition"],
+                               "gb_s_per_gpu_algorithmic": r["value"] / n_gpus * bpc / 1e9,
+                               "frac_of_peak_algorithmic": r["value"] / n_gpus * bpc / 1e9 / peak,
+                               "temp": r["summary"]["temp"]}
+            except Exception as e:  # an extra must never cost the headline line
+                extra[name] = {"error": str(e)[:300]}
 
     # ---------------- CPU baseline (rank 0, N = 1): the oracle port on the host cores ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-        r, w = cpu_port_run(nx, ny, 4, 1)
-        per_iter = max(w / 6.0, 1e-4)
-        cap = max(4, min(2000, int(args.cpu_seconds / per_iter)))
-        r, w = cpu_port_run(nx, ny, cap, 1)
-        cpu = {"value": r["cell_iters"] / w, "unit": "cell-iter/s", "cores": cores, "kind": "port",
-               "sample": "%dx%d mesh, first timestep of the same deck, CG capped at %d iterations, %.1f s" % (
-                   nx, ny, cap, w)}
+        threads = int(os.environ["OMP_NUM_THREADS"])
+        cap, _ = cpu_iters_cap(nx, ny, args.cpu_seconds)
+        ci, w = cpu_port_run(nx, ny, cap, 1)
+        cpu = {"value": ci / w, "unit": "cell-iter/s", "cores": threads, "kind": "port", "host_cpus": cores,
+               "iters_cap": cap,
+               "sample": "%dx%d mesh, first timestep of the same deck, CG capped at %d iterations, solver time only "
+                         "%.1f s, %d OpenMP threads" % (nx, ny, cap, w, threads)}
 
     if rank == 0:
         metric = {"cg": "CG", "cheby": "Chebyshev", "ppcg": "PPCG (outer+inner)", "jacobi": "Jacobi"}[args.solver]
@@ -337,26 +399,63 @@ def main():
                 "config": {"workload": "TeaLeaf %s fp64 %dx%d, standard 5-state deck (tea_bm_5 geometry), "
                                        "eps 1e-15, one timestep per step, %s" % (
                                            metric, nx, ny, "1 GPU" if n_gpus == 1 else
-                                           "%d GPUs %dx%d chunks" % (n_gpus, app.decomposition["x_chunks"],
-                                                                     app.decomposition["y_chunks"])),
-                           "cells_per_gpu": cells // n_gpus, "cg_iterations_per_step": per_step,
+                                           "%d GPUs %dx%d chunks" % (n_gpus, decomposition["x_chunks"],
+                                                                     decomposition["y_chunks"])),
+                           "cells_per_gpu": cells // n_gpus, "cg_iterations_per_step": main_case["per_step"],
                            "l2": "inputs larger than L2: 7 live fields x %.0f MB per GPU" % (ch.x * ch.y * 8 / 1e6),
                            "bytes_per_cell_iter": BYTES_PER_CELL_ITER,
                            "iteration": "cg_calc_pw + cg_calc_ur (96 B/cell moved)"
                            if fused_run
                            else "cg_calc_w + cg_calc_ur + cg_calc_p (104 B/cell moved)"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "wall_s": wall, "summary": summary}
+                "cpu_baseline": cpu, "parity": parity, "extra": extra, "wall_s": wall,
+                "summary": main_case["summary"]}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
         os.dup2(2, 1)
-    app.close()
-    if comms:
-        comms.finalise()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def parity_leg(L, new_comms, world, rank, local_rank, sum_over_ranks):
+    """Decomposed 250x250 CG deck (3 timesteps; three-kernel and fused resident loops) vs the CPU oracle's
+    N-chunk run with the GPU summation order: every rank must hold the oracle's iteration counts, per-step
+    residuals and the four summary sums bit for bit.  Then 60 back-to-back halo exchanges of changing field
+    sets / depths, generated and verified cell by cell on the device (tl_halo_stress)."""
+    from exploringsycl_b200 import TeaLeaf, read_config
+    from exploringsycl_b200._lib import check
+    from oracle import oracle as O
+    os.environ.setdefault("OMP_NUM_THREADS", str(max(1, (os.cpu_count() or 1) // max(world, 1))))
+    ores = O.run_deck(O.make_deck(250, end_step=3, num_chunks=world), gpu_sum_order=True)
+    bad, halo_bad = 0, None
+    detail = {}
+    for label, fuse in (("three_kernel", 0), ("fused", 2)):
+        s, states = read_config(os.path.join(ROOT, "tests", "decks", "tea_250_cg.in"))
+        s.end_step, s.fuse_p_into_w = 3, fuse
+        comms = new_comms()
+        app = TeaLeaf(s, states, comms, device=local_rank)
+        summary = app.diffuse()
+        ok = ([h["iters_a"] for h in app.history] == ores["iters_a"]
+              and [h["error"] for h in app.history] == ores["error"]
+              and all(summary[k] == ores[k] for k in ("vol", "mass", "ie", "temp")))
+        bad += 0 if ok else 1
+        detail[label] = {"iters": [h["iters_a"] for h in app.history], "temp": summary["temp"]}
+        if world > 1 and fuse == 2:
+            n = C.c_long(-1)
+            check(L.tl_halo_stress(app.chunk.handle, comms.handle, 250, 250, 60, 2, C.byref(n)))
+            halo_bad = n.value
+        app.close()
+        if comms:
+            comms.finalise()
+    bad_all = int(sum_over_ranks(float(bad)))
+    halo_all = None if halo_bad is None else int(sum_over_ranks(float(halo_bad)))
+    return {"n_chunk_bit_exact": bad_all == 0, "halo_bit_exact": None if halo_all is None else halo_all == 0,
+            "chunks": world, "oracle_iters": ores["iters_a"], "oracle_temp": ores["temp"], "gpu": detail,
+            "what": "tea_250_cg deck, 3 timesteps, decomposed over %d rank(s): CG iteration counts, per-step rrn and "
+                    "vol/mass/ie/temp equal the CPU oracle's %d-chunk run bit for bit (three-kernel and fused loops); "
+                    "60 back-to-back halo exchanges verified on the device" % (world, world)}
 
 
 if __name__ == "__main__":

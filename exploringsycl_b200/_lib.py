@@ -89,6 +89,7 @@ SIGNATURES = {
     "tl_comms_rank": ([_vp], _i),
     "tl_comms_size": ([_vp], _i),
     "tl_comms_barrier": ([_vp], _i),
+    "tl_comms_abort": ([_vp], _i),
     "tl_comms_sum": ([_vp, _pd], _i),
     "tl_comms_min": ([_vp, _pd], _i),
     "tl_comms_send_recv": ([_vp, _dp, _dp, _i, _i, _i, _i], _i),
@@ -97,7 +98,9 @@ SIGNATURES = {
     "tl_comms_attach_chunk": ([_vp, _vp], _i),
     "tl_decompose": ([_i, _i, _i, _i, _pi, _pi, _pi, _pi, _i4, _pi, _pi], _i),
     "tl_halo_update": ([_vp, _vp, _i6, _i], _i),
+    "tl_halo_stress": ([_vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_long)], _i),
     "tl_solve_opts_default": ([C.POINTER(TlSolveOpts)], None),
+    "tl_cg_loop_is_fused": ([_vp, _i], _i),
     "tl_solve": ([_vp, _vp, C.POINTER(TlSolveOpts), _d, _d, C.POINTER(TlSolveInfo)], _i),
     "tl_timestep": ([_vp, _vp, C.POINTER(TlSolveOpts), _d, _d, _d, C.POINTER(TlSolveInfo)], _i),
     "tl_field_summary": ([_vp, _vp, _pd, _pd, _pd, _pd], _i),

@@ -3,6 +3,7 @@
 // synchronously through a double*, with the reference's accumulate-vs-assign convention
 // (+= for rro, pw; = for rrn, norm, error, summary).
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdlib.h>
 #include <string.h>
 #include "tl_internal.h"
@@ -92,6 +93,13 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
     TL_CUDA(cudaMemset(c->scal, 0, sizeof(DevScal)));
     TL_CUDA(cudaMallocHost((void**)&c->scal_h, 3 * sizeof(DevScal)));
     memset(c->scal_h, 0, 3 * sizeof(DevScal));
+    {   // host-mapped error word: device-side peer waits that time out mark it (spin_flag in tl_kernels.cu)
+        TL_CUDA(cudaHostAlloc((void**)&c->err_h, 64, cudaHostAllocMapped));
+        *c->err_h = 0u;
+        unsigned int* dptr = nullptr;
+        TL_CUDA(cudaHostGetDevicePointer((void**)&dptr, c->err_h, 0));
+        TL_CUDA(cudaMemcpy((char*)c->scal + offsetof(DevScal, err_host), &dptr, sizeof(dptr), cudaMemcpyHostToDevice));
+    }
     TL_TRY(dev_zalloc(&c->d_alphas, max_iters + 1));
     TL_TRY(dev_zalloc(&c->d_betas, max_iters + 1));
     // kernel_initialise.cpp:76-79: host coefficient arrays of max_iters doubles, zeroed
@@ -123,7 +131,7 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     for (int f = 0; f < TL_NUM_FIELDS; ++f)
         if (c->alt_alloc[f]) cudaFree(c->alt_alloc[f]);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
-    cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h);
+    cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h); cudaFreeHost(c->err_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas);
     free(c->cg_alphas); free(c->cg_betas); free(c->cheby_alphas); free(c->cheby_betas);
     for (int fc = 0; fc < 4; ++fc) { cudaFree(c->face_send[fc]); cudaFree(c->face_recv[fc]); }
@@ -148,7 +156,7 @@ extern "C" int tl_chunk_sync(tl_chunk* c)
     TL_CHECK_ARG(c, "null chunk");
     TL_CUDA(cudaSetDevice(c->device));
     TL_CUDA(cudaStreamSynchronize(c->stream));
-    return TL_OK;
+    return tl_check_peer_timeout(c);
 }
 
 extern "C" int tl_field_write(tl_chunk* c, int field, const double* host)
@@ -170,7 +178,7 @@ extern "C" int tl_field_read(tl_chunk* c, int field, double* host)
     TL_CUDA(cudaMemcpy2DAsync(host, (size_t)g.x * 8, c->f[field] + g.off, (size_t)g.pitch * 8,
                               (size_t)g.x * 8, g.y, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
-    return TL_OK;
+    return tl_check_peer_timeout(c);
 }
 
 extern "C" int tl_array_read(tl_chunk* c, int array, double* host)
@@ -189,11 +197,21 @@ extern "C" double* tl_cg_betas(tl_chunk* c) { return c ? c->cg_betas : nullptr; 
 extern "C" double* tl_cheby_alphas(tl_chunk* c) { return c ? c->cheby_alphas : nullptr; }
 extern "C" double* tl_cheby_betas(tl_chunk* c) { return c ? c->cheby_betas : nullptr; }
 
+int tl_check_peer_timeout(tl_chunk* c)
+{
+    if (c->err_h && *(volatile unsigned int*)c->err_h == 0xdeadu) {
+        tl_set_error("a device-side wait for a peer rank timed out (halo exchange or resident solver loop): "
+                     "the results of this chunk are not valid");
+        return TL_ERR_COMMS;
+    }
+    return TL_OK;
+}
+
 int tl_fetch_scal(tl_chunk* c)
 {
     TL_CUDA(cudaMemcpyAsync(c->scal_h, c->scal, sizeof(DevScal), cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
-    return TL_OK;
+    return tl_check_peer_timeout(c);
 }
 
 #define ENTER(c)                                  \

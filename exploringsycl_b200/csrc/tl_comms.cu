@@ -40,6 +40,7 @@ struct ShmHeader {
     int num_ranks;
     std::atomic<unsigned int> bar_count;
     std::atomic<unsigned int> bar_gen;
+    std::atomic<int> aborted;                 // tl_comms_abort(): every blocked or later host wait fails at once
     double red[2][TLC_MAX_RANKS];
     std::atomic<int> nb_list[TLC_MAX_RANKS][4]; // neighbour ranks each rank sends to (registered lazily)
     // GPU arenas
@@ -69,7 +70,7 @@ struct tl_comms {
     void* peer_pfield[TLC_MAX_RANKS];
     void* peer_arena_base[TLC_MAX_RANKS];  // what cudaIpcOpenMemHandle returned (to close)
     void* peer_pfield_base[TLC_MAX_RANKS];
-    unsigned long long xchg_seq; // exchange phases completed
+    unsigned long long face_seq[4]; // halo messages exchanged over each of my faces (same count on both ends)
     unsigned long long res_seq;  // resident-loop iterations launched so far (slot / halo flag base)
 };
 
@@ -88,6 +89,10 @@ static const double TLC_TIMEOUT_S = 60.0;
         unsigned long spins_ = 0;                                           \
         while (!(cond)) {                                                   \
             if ((++spins_ & 0x3ff) == 0) {                                  \
+                if (k->hdr && k->hdr->aborted.load(std::memory_order_acquire)) { \
+                    tl_set_error("comms: a peer rank aborted (while waiting for %s)", what); \
+                    return TL_ERR_COMMS;                                    \
+                }                                                           \
                 sched_yield();                                              \
                 if (now_s() - t0_ > TLC_TIMEOUT_S) {                        \
                     tl_set_error("comms timeout waiting for %s", what);     \
@@ -179,6 +184,14 @@ extern "C" int tl_comms_destroy(tl_comms* k)
     if (k->arena) cudaFree(k->arena);
     munmap(k->hdr, k->shm_bytes);
     delete k;
+    return TL_OK;
+}
+
+// abort_comms(), comms.c:79-82 (MPI_Abort): poisons the shared header so that the other ranks' host-side waits
+// (barrier, reductions, mailboxes) fail with TL_ERR_COMMS at once instead of running into their time-outs.
+extern "C" int tl_comms_abort(tl_comms* k)
+{
+    if (k && k->hdr) k->hdr->aborted.store(1, std::memory_order_release);
     return TL_OK;
 }
 
@@ -365,15 +378,17 @@ static int block_offset(const void* ptr, unsigned long long* off)
 //   tail+4..7   p-halo flags of the resident CG loop (by receiving face)
 //   tail+8..39  reduction slots  [kind][parity][rank]
 //   tail+40..71 reduction flags  [kind][parity][rank]
+//   tail+72..75 ack flags of the generic halo exchange (by SENDING face: "message n of this face was unpacked")
 static size_t arena_recv_off(const tl_comms* k, int face, int parity)
 {
     return ((size_t)face * 2 + parity) * k->face_elems;
 }
 static size_t arena_flags_off(const tl_comms* k) { return (size_t)8 * k->face_elems; }
-static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 128; }
+static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 256; }
 #define ARENA_HFLAGS 4
 #define ARENA_SLOTS 8
 #define ARENA_SFLAGS 40
+#define ARENA_ACKS 72
 
 extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
 {
@@ -450,10 +465,13 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
         const int n = c->nb[f];
         c->nb_recv[f] = nullptr;
         c->nb_flag[f] = nullptr;
+        c->nb_ack[f] = nullptr;
+        c->my_ack[f] = (unsigned long long*)(tail + ARENA_ACKS) + f;
         if (n == TL_EXTERNAL_FACE) continue;
         double* base = (double*)k->peer_arena[n];
         c->nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
         c->nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
+        c->nb_ack[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_ACKS) + opposite[f];
         mc.nb_p[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_P * h->field_elems[n];
         mc.nb_r[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_R * h->field_elems[n];
         mc.nb_hflag[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_HFLAGS) + opposite[f];
@@ -475,27 +493,6 @@ unsigned long long tlc_resident_seq_advance(tl_comms* k, int launched)
     return base;
 }
 
-__global__ void k_signal(unsigned long long* remote_flag, unsigned long long v)
-{
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote_flag), "l"(v) : "memory");
-}
-
-__global__ void k_wait(unsigned long long* flag, unsigned long long v, DevScal* S)
-{
-    unsigned long long cur;
-    const long long t0 = clock64();
-    for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
-        if (cur >= v) break;
-        if (clock64() - t0 > 10000000000LL) { // ~5 s: give up rather than hang the GPU
-            S->pad = 0xdeadu;
-            break;
-        }
-        __nanosleep(200);
-    }
-}
-
 // remote_halo_driver.c:11-129 over NVLink: L/R fully completes (incl. unpack) before B/T packs.
 int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth)
 {
@@ -507,29 +504,114 @@ int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth)
         tl_set_error("halo exchange needs an attached GPU comms endpoint");
         return TL_ERR_COMMS;
     }
+    // TL_TEST_SKEW="rank:microseconds": that rank's host sleeps between the send and the unpack launches of every
+    // phase (tests only: widens the window in which a neighbour can run ahead by one exchange)
+    static int skew_rank = -2, skew_us = 0;
+    if (skew_rank == -2) {
+        skew_rank = -1;
+        const char* e = getenv("TL_TEST_SKEW");
+        if (e) sscanf(e, "%d:%d", &skew_rank, &skew_us);
+    }
     for (int phase = 0; phase < 2; ++phase) {
         const int f0 = phase ? TL_FACE_BOTTOM : TL_FACE_LEFT;
-        const unsigned long long seq = ++k->xchg_seq;
-        const int par = (int)(seq & 1ull);
         int faces[2];
         double* sbuf[2];
         double* rbuf[2];
         unsigned long long* sflag[2];
         unsigned long long* rflag[2];
+        unsigned long long* sack[2];
+        unsigned long long* rack[2];
+        unsigned long long seqs[2];
         for (int q = 0; q < 2; ++q) {
             const int f = f0 + q;
             const bool has = (c->nb[f] != TL_EXTERNAL_FACE);
+            // message number on this face: both ends count the same exchanges, and consecutive messages of a face
+            // alternate between its two receive buffers
+            seqs[q] = has ? ++k->face_seq[f] : 0ull;
+            const int par = (int)(seqs[q] & 1ull);
             faces[q] = has ? f : -1;
             sbuf[q] = has ? c->nb_recv[f] + (size_t)par * k->face_elems : nullptr;
             sflag[q] = has ? c->nb_flag[f] : nullptr;
+            sack[q] = has ? c->my_ack[f] : nullptr;
             rbuf[q] = has ? k->arena + arena_recv_off(k, f, par) : nullptr;
             rflag[q] = has ? (unsigned long long*)(k->arena + arena_flags_off(k)) + f : nullptr;
+            rack[q] = has ? c->nb_ack[f] : nullptr;
         }
         if (faces[0] < 0 && faces[1] < 0) continue;
         // pack both faces of the phase into the neighbours' buffers + release their flags: one launch;
-        // acquire my flags + unpack: one launch (remote_halo_driver.c:24-126 order: L/R done before B/T packs)
-        TL_TRY(tlk_phase_exchange(c, fields, depth, true, faces, sbuf, sflag, seq));
-        TL_TRY(tlk_phase_exchange(c, fields, depth, false, faces, rbuf, rflag, seq));
+        // acquire my flags + unpack + hand the buffers back: one launch (remote_halo_driver.c:24-126 order: L/R done
+        // before B/T packs)
+        TL_TRY(tlk_phase_exchange(c, fields, depth, true, faces, sbuf, sflag, sack, seqs));
+        if (skew_rank == k->rank && skew_us > 0) usleep(skew_us);
+        TL_TRY(tlk_phase_exchange(c, fields, depth, false, faces, rbuf, rflag, rack, seqs));
     }
     return TL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Halo-exchange stress (tests/test_multigpu.py): `reps` back-to-back exchanges with NO host synchronisation in
+// between.  Before exchange t a kernel fills the interior of the fields with a pattern of (global cell, t, field); after
+// it a kernel compares every cell within `depth` of the interior (corners included) with what
+// remote_halo_driver.c:24-126 + local_halos.cpp must have produced -- the neighbour's cell, or the reflection at the
+// edge of the global mesh -- and counts mismatches on the device.  A receive buffer that is overwritten before it was
+// unpacked, or unpacked twice, shows up as a mismatch of exchange t against the data of exchange t +- 1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double stress_value(int gx, int gy, int rep, int field)
+{
+    return (double)gx + 10000.0 * (double)gy + 0.25 * (double)rep + 1.0e8 * (double)field;
+}
+__global__ void k_stress_fill(Geo g, double* f, int left, int bottom, int rep, int field)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y;
+    if (kk >= g.x) return;
+    const bool interior = kk >= g.hd && kk < g.x - g.hd && jj >= g.hd && jj < g.y - g.hd;
+    f[(long)g.off + (long)jj * g.pitch + kk] =
+        interior ? stress_value(left + kk - g.hd, bottom + jj - g.hd, rep, field) : -777.0;
+}
+__global__ void k_stress_check(Geo g, const double* f, int left, int bottom, int gx_cells, int gy_cells, int depth,
+                               int rep, int field, unsigned long long* mismatches)
+{
+    const int kk = blockIdx.x * blockDim.x + threadIdx.x, jj = blockIdx.y;
+    const int lo = g.hd - depth;
+    if (kk < lo || kk >= g.x - lo || jj < lo || jj >= g.y - lo) return;
+    int gx = left + kk - g.hd, gy = bottom + jj - g.hd;
+    gx = gx < 0 ? -gx - 1 : (gx >= gx_cells ? 2 * gx_cells - gx - 1 : gx);
+    gy = gy < 0 ? -gy - 1 : (gy >= gy_cells ? 2 * gy_cells - gy - 1 : gy);
+    if (__ldcg(f + (long)g.off + (long)jj * g.pitch + kk) != stress_value(gx, gy, rep, field))
+        atomicAdd(mismatches, 1ull);
+}
+
+extern "C" int tl_halo_stress(tl_chunk* c, tl_comms* k, int grid_x_cells, int grid_y_cells, int reps, int depth,
+                              long* mismatches)
+{
+    TL_CHECK_ARG(c && k && mismatches && reps > 0 && depth >= 1 && depth <= c->g.hd, "bad arguments");
+    TL_CUDA(cudaSetDevice(c->device));
+    unsigned long long* d_bad = nullptr;
+    TL_CUDA(cudaMalloc((void**)&d_bad, sizeof(unsigned long long)));
+    TL_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+    const int fields[2] = {TL_FIELD_U, TL_FIELD_DENSITY};
+    int flags[TL_NUM_EXCHANGE_FIELDS] = {0, 0, 0, 0, 0, 0};
+    dim3 grid((c->g.x + 127) / 128, c->g.y);
+    for (int rep = 0; rep < reps; ++rep) {
+        // alternate the field set and the depth: consecutive messages of a face differ in length and content
+        const int nf = (rep & 1) ? 2 : 1;
+        const int d = (rep % 3 == 2) ? 1 : depth;
+        for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i) flags[i] = 0;
+        for (int q = 0; q < nf; ++q) {
+            flags[fields[q]] = 1;
+            k_stress_fill<<<grid, 128, 0, c->stream>>>(c->g, c->f[fields[q]], c->left, c->bottom, rep, fields[q]);
+        }
+        TL_TRY(tl_halo_update(c, k, flags, d));
+        for (int q = 0; q < nf; ++q)
+            k_stress_check<<<grid, 128, 0, c->stream>>>(c->g, c->f[fields[q]], c->left, c->bottom, grid_x_cells,
+                                                        grid_y_cells, d, rep, fields[q], d_bad);
+        g_tl_launches += 2 * nf;
+    }
+    TL_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    TL_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+    TL_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_bad);
+    *mismatches = (long)bad;
+    return tl_check_peer_timeout(c);
 }

@@ -39,6 +39,8 @@ struct DevScal {
     unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
     unsigned int pad;        // 0xdead: a peer wait timed out
     unsigned long long dbg[4]; // first timed-out wait: site, wanted value, seen value, block id
+    unsigned int* err_host;  // mapped pinned host word: 0xdead is stored there as well, so the host sees a
+                             // timed-out wait at its next synchronisation point without fetching DevScal
 };
 
 // Multi-rank context of the resident CG loop (passed by value to the hot kernels; num_ranks == 1
@@ -103,6 +105,9 @@ struct tl_chunk {
     MultiCtx mc;                  // template filled by tl_comms_attach_chunk (tl/it_global/sbase/hbase per launch)
     double* nb_recv[4];           // neighbours' receive buffers of the generic halo exchange (peer-mapped)
     unsigned long long* nb_flag[4];
+    unsigned long long* nb_ack[4];   // neighbour's "buffer consumed" flag for what it SENDS to my face f (I release it)
+    unsigned long long* my_ack[4];   // the same kind of flag for what I send through face f (the neighbour releases it)
+    unsigned int* err_h;             // pinned + mapped host word behind DevScal.err_host
     bool has_peers;
     int resident_iters;           // CG iterations enqueued so far in the current solve (host bookkeeping)
 };
@@ -143,7 +148,8 @@ int tlk_field_summary(tl_chunk* c);                       // -> scal->sums[0..3]
 int tlk_local_halos(tl_chunk* c, const int fields[6], int depth);
 int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pack, double* devbuf, int* len);
 int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, const int faces[2], double* const bufs[2],
-                       unsigned long long* const flags[2], unsigned long long seq);
+                       unsigned long long* const flags[2], unsigned long long* const acks[2],
+                       const unsigned long long seqs[2]);
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr);                // -> scal->pw (& alpha when SCAL_DEV)
 int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false); // -> scal->rrn (& beta, conv when SCAL_DEV)
@@ -168,3 +174,5 @@ int tlk_seed_rro(tl_chunk* c);                            // scal->rro = scal->s
 
 // fetch the DevScal to the pinned mirror and wait
 int tl_fetch_scal(tl_chunk* c);
+// TL_ERR_COMMS if a device-side wait for a peer rank has timed out since the chunk was created
+int tl_check_peer_timeout(tl_chunk* c);

@@ -51,8 +51,10 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p)
     asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
-// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU: on timeout an
-// error mark is left in DevScal.pad and the caller carries on with whatever is there.
+// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU.  A timeout
+// is FATAL for the solve: the error mark goes to DevScal.pad and to the host-mapped error word, and the convergence stamp is
+// set so that every later launch of the resident loop returns at once; the host reports TL_ERR_COMMS at its next
+// synchronisation point (tl_check_peer_timeout).
 __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
                                           unsigned long long site = 0)
 {
@@ -66,11 +68,30 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
                 S->dbg[1] = want;
                 S->dbg[2] = seen;
                 S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
+                S->conv = 1;
+                S->conv_iter = 0; // mc_skip() is now true for every iteration: nothing computes on unknown data
+                if (S->err_host) *(volatile unsigned int*)S->err_host = 0xdeadu;
+                __threadfence_system();
             }
             break;
         }
         __nanosleep(64);
     }
+}
+// Loads of data that a peer GPU may store while this kernel runs (halo cells of p / r in the multi-rank loop): ld.global.cg
+// is served by L2, the point of coherence for NVLink peer stores; the non-coherent path (ld.global.nc / L1) could return a
+// sector fetched before the neighbour's flag arrived.  Single-rank instantiations keep the read-only path.
+template <bool COH>
+__device__ __forceinline__ double2 ldp2(const double* p)
+{
+    if constexpr (COH) return __ldcg(reinterpret_cast<const double2*>(p));
+    else return __ldg(reinterpret_cast<const double2*>(p));
+}
+template <bool COH>
+__device__ __forceinline__ double ldp1(const double* p)
+{
+    if constexpr (COH) return __ldcg(p);
+    else return __ldg(p);
 }
 struct RedArgs {
     double* partials;   // [NR][cap]   one per tile
@@ -431,11 +452,19 @@ int tlk_pack_face(tl_chunk* c, const int fields[6], int depth, int face, bool pa
 // One launch per exchange phase and direction: both faces of a phase (L+R or B+T) and all flagged fields.
 //   k_pack_send   : gathers into the NEIGHBOUR's receive buffer (peer-mapped, NVLink stores); the last CTA
 //                   to finish releases the neighbours' arrival flags (every CTA fences its stores first).
-//   k_wait_unpack : thread 0 of each CTA acquires its face's arrival flag, then the CTA scatters.
+//   k_wait_unpack : thread 0 of each CTA acquires its face's arrival flag, then the CTA scatters; the last CTA
+//                   to finish releases the senders' "consumed" (ack) flags.
+// Message n of a face (n = 1, 2, ...: a per-face counter, identical on both ends) travels through receive buffer
+// n & 1 and raises the arrival flag to n.  The sender of message n first acquires ack >= n - 2: the message that last
+// used that buffer has been unpacked.  (With a symmetric exchange the two buffers alone already guarantee this --
+// send(n+2) follows my unpack(n+1), which follows the neighbour's send(n+1), which follows its unpack(n) -- the ack
+// makes it hold without that argument, e.g. under rank skew with one-directional traffic.)
 struct PhaseFaces {
     int face[2];                  // TL_FACE_* or -1
-    double* buf[2];               // pack: neighbour's receive buffer; unpack: my receive buffer
+    double* buf[2];               // pack: neighbour's receive buffer (parity n & 1); unpack: mine
     unsigned long long* flag[2];  // pack: neighbour's arrival flag;   unpack: my arrival flag
+    unsigned long long* ack[2];   // pack: my ack flag (the neighbour releases it); unpack: the sender's ack flag
+    unsigned long long seq[2];    // n
 };
 
 __device__ __forceinline__ long halo_cell_index(const Geo& g, int face, int depth, int pack, int b)
@@ -456,16 +485,20 @@ __device__ __forceinline__ long halo_cell_index(const Geo& g, int face, int dept
     return (long)g.off + (long)jj * g.pitch + kk;
 }
 
-__global__ void k_pack_send(Geo g, FieldList fl, int depth, PhaseFaces pf, unsigned long long seq, DevScal* S)
+__global__ void k_pack_send(Geo g, FieldList fl, int depth, PhaseFaces pf, DevScal* S)
 {
-    const int face = pf.face[blockIdx.z];
+    const int q = blockIdx.z;
+    const int face = pf.face[q];
     if (face >= 0) {
+        if (pf.seq[q] > 2ull) { // block-uniform
+            if (threadIdx.x == 0) spin_flag(pf.ack[q], pf.seq[q] - 2ull, S, 60ull + face);
+            __syncthreads();
+        }
         const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
         const int per_field = depth * (lr ? g.y : g.x);
         const int b = blockIdx.x * blockDim.x + threadIdx.x;
         if (b < per_field)
-            pf.buf[blockIdx.z][(size_t)blockIdx.y * per_field + b] =
-                fl.f[blockIdx.y][halo_cell_index(g, face, depth, 1, b)];
+            pf.buf[q][(size_t)blockIdx.y * per_field + b] = fl.f[blockIdx.y][halo_cell_index(g, face, depth, 1, b)];
     }
     __shared__ int s_last;
     __threadfence_system();
@@ -477,27 +510,43 @@ __global__ void k_pack_send(Geo g, FieldList fl, int depth, PhaseFaces pf, unsig
     __syncthreads();
     if (s_last && threadIdx.x < 2) {
         if (threadIdx.x == 0) S->counter[2] = 0u;
-        if (pf.face[threadIdx.x] >= 0) st_release_sys(pf.flag[threadIdx.x], seq);
+        if (pf.face[threadIdx.x] >= 0) st_release_sys(pf.flag[threadIdx.x], pf.seq[threadIdx.x]);
     }
 }
 
-__global__ void k_wait_unpack(Geo g, FieldList fl, int depth, PhaseFaces pf, unsigned long long seq, DevScal* S)
+__global__ void k_wait_unpack(Geo g, FieldList fl, int depth, PhaseFaces pf, DevScal* S)
 {
-    const int face = pf.face[blockIdx.z];
-    if (face < 0) return;
-    if (threadIdx.x == 0) spin_flag(pf.flag[blockIdx.z], seq, S, 50ull + face);
+    const int q = blockIdx.z;
+    const int face = pf.face[q];
+    if (face >= 0) { // block-uniform
+        if (threadIdx.x == 0) spin_flag(pf.flag[q], pf.seq[q], S, 50ull + face);
+        __syncthreads();
+        const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
+        const int per_field = depth * (lr ? g.y : g.x);
+        const int b = blockIdx.x * blockDim.x + threadIdx.x;
+        if (b < per_field)
+            fl.f[blockIdx.y][halo_cell_index(g, face, depth, 0, b)] =
+                __ldcg(pf.buf[q] + (size_t)blockIdx.y * per_field + b);
+    }
+    // every CTA's reads of the receive buffer are complete before its ticket; the last one hands the buffers back
+    __shared__ int s_last;
+    __threadfence();
     __syncthreads();
-    const bool lr = (face == TL_FACE_LEFT || face == TL_FACE_RIGHT);
-    const int per_field = depth * (lr ? g.y : g.x);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < per_field)
-        fl.f[blockIdx.y][halo_cell_index(g, face, depth, 0, b)] =
-            __ldcg(pf.buf[blockIdx.z] + (size_t)blockIdx.y * per_field + b);
+    if (threadIdx.x == 0) {
+        const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+        s_last = (atomicAdd(&S->counter[3], 1u) == total - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 2) {
+        if (threadIdx.x == 0) S->counter[3] = 0u;
+        if (pf.face[threadIdx.x] >= 0) st_release_sys(pf.ack[threadIdx.x], pf.seq[threadIdx.x]);
+    }
 }
 
-// faces/bufs/flags: two entries (one per face of the phase; face -1 = no neighbour on that side)
+// faces/bufs/flags/acks/seqs: two entries (one per face of the phase; face -1 = no neighbour on that side)
 int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, const int faces[2], double* const bufs[2],
-                       unsigned long long* const flags[2], unsigned long long seq)
+                       unsigned long long* const flags[2], unsigned long long* const acks[2],
+                       const unsigned long long seqs[2])
 {
     FieldList fl;
     fl.n = 0;
@@ -510,6 +559,8 @@ int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, c
         pf.face[q] = faces[q];
         pf.buf[q] = bufs[q];
         pf.flag[q] = flags[q];
+        pf.ack[q] = acks[q];
+        pf.seq[q] = seqs[q];
         if (faces[q] >= 0) {
             const bool lr = (faces[q] == TL_FACE_LEFT || faces[q] == TL_FACE_RIGHT);
             const int n = depth * (lr ? c->g.y : c->g.x);
@@ -517,8 +568,8 @@ int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, c
         }
     }
     dim3 grid((per_field + 127) / 128, fl.n, 2);
-    if (send) k_pack_send<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, seq, c->scal);
-    else k_wait_unpack<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, seq, c->scal);
+    if (send) k_pack_send<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, c->scal);
+    else k_wait_unpack<<<grid, 128, 0, c->stream>>>(c->g, fl, depth, pf, c->scal);
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     return TL_OK;
@@ -588,6 +639,7 @@ __global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
     S->counter[0] = 0u;
     S->counter[1] = 0u;
     S->counter[2] = 0u;
+    S->counter[3] = 0u;
 }
 int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
 {
@@ -764,7 +816,7 @@ static int hot_check(const tl_chunk* c, dim3 grid)
 // slide through registers, so every element is requested from L2 once per tile.
 template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
-k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, const double* __restrict__ ky,
+k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double* __restrict__ ky,
             double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev,
             const MultiCtx mc)
 {
@@ -780,7 +832,10 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
         __shared__ int s_skip;
         if (threadIdx.x == 0) {
             s_skip = mc_skip(mc, S) ? 1 : 0;
-            if (!s_skip && mc.tl > 0) {
+            // The halo of p consumed by iteration it_global > 0 was stored by the neighbours' calc_p of iteration
+            // it_global - 1.  That holds for the first launch of a re-entered resident call too (cg_presteps steps one
+            // iteration at a time with no exchange in between): the previous call's last calc_p released hbase.
+            if (!s_skip && (mc.tl > 0 || mc.it_global > 0)) {
                 const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
                 const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
                 const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
@@ -798,9 +853,9 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
     if (t.v0) {
         long i = t.i;
         const long pitch = g.pitch;
-        double2 pm = ld2_ro(p + i - pitch);
-        double2 pc = ld2_ro(p + i);
-        double pl = __ldg(p + i - 1), pr = __ldg(p + i + 2);
+        double2 pm = ldp2<MULTI>(p + i - pitch);
+        double2 pc = ldp2<MULTI>(p + i);
+        double pl = ldp1<MULTI>(p + i - 1), pr = ldp1<MULTI>(p + i + 2);
         double2 kyc = ld2_ro(ky + i);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             double2 pn[U], kyn[U], kxc[U];
@@ -809,12 +864,12 @@ k_cg_calc_w(Geo g, const double* __restrict__ p, const double* __restrict__ kx, 
             for (int u = 0; u < U; ++u) {
                 if (jb + u < t.j1) {
                     const long iu = i + u * pitch;
-                    pn[u] = ld2_ro(p + iu + pitch);
+                    pn[u] = ldp2<MULTI>(p + iu + pitch);
                     kyn[u] = ld2_ro(ky + iu + pitch);
                     kxc[u] = ld2_ro(kx + iu);
                     kxr[u] = __ldg(kx + iu + 2);
-                    pln[u] = __ldg(p + iu + pitch - 1);
-                    prn[u] = __ldg(p + iu + pitch + 2);
+                    pln[u] = ldp1<MULTI>(p + iu + pitch - 1);
+                    prn[u] = ldp1<MULTI>(p + iu + pitch + 2);
                 }
             }
 #pragma unroll
@@ -1189,7 +1244,7 @@ int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_h
 // buffered: reads come from p_in, writes go to p_out (the chunk's P and P2 buffers swap roles).
 template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
-k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out, const double* __restrict__ r,
+k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double* r,
              const double* __restrict__ kx, const double* __restrict__ ky, double* __restrict__ w,
              double* __restrict__ d_alphas, double* __restrict__ d_betas, RedArgs ra, int rows, int rev, int ext_mask,
              const MultiCtx mc)
@@ -1258,13 +1313,13 @@ k_cg_calc_pw(Geo g, const double* __restrict__ p_in, double* __restrict__ p_out,
     const bool halo_l = MULTI && t.v0 && !(ext_mask & 1) && t.kk == klo;
     const bool halo_r = MULTI && !(ext_mask & 2) && ((t.v1 && t.kk + 1 == khi) || (t.v0 && !t.v1 && t.kk == khi));
     auto pnew2 = [&](long i) {
-        double2 a = ld2_ro(p_in + i);
-        const double2 b = ld2_ro(r + i);
+        double2 a = ldp2<MULTI>(p_in + i);
+        const double2 b = ldp2<MULTI>(r + i);
         a.x = beta * a.x + b.x;
         a.y = beta * a.y + b.y;
         return a;
     };
-    auto pnew1 = [&](long i) { return beta * __ldg(p_in + i) + __ldg(r + i); };
+    auto pnew1 = [&](long i) { return beta * ldp1<MULTI>(p_in + i) + ldp1<MULTI>(r + i); };
     // sides of an updated row held as double2 `c` in every lane
     auto sides = [&](double2 c, long i, double& l, double& rr) {
         const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);

@@ -36,7 +36,8 @@ extern "C" int tl_halo_update(tl_chunk* c, tl_comms* k, const int fields_to_exch
     for (int i = 0; i < TL_NUM_EXCHANGE_FIELDS; ++i) any |= (fields_to_exchange[i] != 0);
     if (!any) return TL_OK;
     TL_TRY(tlc_halo_exchange(c, k, fields_to_exchange, depth));
-    return tlk_local_halos(c, fields_to_exchange, depth);
+    TL_TRY(tlk_local_halos(c, fields_to_exchange, depth));
+    return tl_check_peer_timeout(c); // no sync here: reports a time-out of any EARLIER wait of this chunk
 }
 
 extern "C" void tl_solve_opts_default(tl_solve_opts* o)
@@ -277,6 +278,20 @@ static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, d
     return TL_OK;
 }
 
+// Which form of the resident CG iteration runs for this chunk and option value (same answer on every rank of a
+// decomposition; results are bit-identical either way):
+//   one rank                      fused (calc_pw + calc_ur) unless fuse_p_into_w == 0
+//   several ranks, option 2       fused, r's halo travels
+//   several ranks, option 1 auto  fused when the decomposition has no left/right neighbours (1 x N: measured +2.5 % at
+//                                 N = 2); with left/right neighbours the three-kernel form was faster (+6 % at 2 x 4)
+extern "C" int tl_cg_loop_is_fused(const tl_chunk* c, int fuse_p_into_w)
+{
+    if (!c || fuse_p_into_w == 0) return 0;
+    if (!c->has_peers) return 1;
+    const bool lr_nb = c->nb[TL_FACE_LEFT] != TL_EXTERNAL_FACE || c->nb[TL_FACE_RIGHT] != TL_EXTERNAL_FACE;
+    return (fuse_p_into_w == 2 || !lr_nb) ? 1 : 0;
+}
+
 static bool use_resident_multi(const tl_chunk* c, tl_comms* k)
 {
     const char* e = getenv("TL_MULTI_HOST_DRIVEN");
@@ -314,11 +329,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
         TL_TRY(tl_halo_update(c, k, fields, 1));
         TL_TRY(fetch_cg_coeffs(c, S->iters));
     } else if (use_resident_multi(c, k)) {
-        // fuse_p_into_w == 1 (auto): the two-kernel form wins when no left/right neighbour exists (1 x N
-        // decompositions: measured +2.5 % at N = 2); with left/right neighbours the three-kernel form is
-        // faster (measured +6 % at N = 8, 2 x 4).  The test is the same on every rank of a decomposition.
-        const bool lr_nb = c->nb[TL_FACE_LEFT] != TL_EXTERNAL_FACE || c->nb[TL_FACE_RIGHT] != TL_EXTERNAL_FACE;
-        const bool fuse_multi = o->fuse_p_into_w == 2 || (o->fuse_p_into_w == 1 && !lr_nb);
+        const bool fuse_multi = tl_cg_loop_is_fused(c, o->fuse_p_into_w) != 0;
         TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches, fuse_multi));
         const DevScal* S = c->scal_h;
         error = S->error;
@@ -695,10 +706,7 @@ extern "C" int tl_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         info->gpu_ms = ms;
-        if (c->scal_h->pad == 0xdeadu) {
-            tl_set_error("halo exchange timed out waiting for a neighbour");
-            rc = TL_ERR_COMMS;
-        }
+        rc = tl_check_peer_timeout(c); // the stream is idle: every wait of this solve has either passed or marked the word
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -746,6 +754,10 @@ extern "C" int tl_timestep(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, dou
     }
     TL_TRY(tl_halo_update(c, k, fields, 1));
     info->kernel_launches += g_tl_launches - l0;
+    if (k && tl_comms_size(k) > 1) { // the final exchange of the step waits for the neighbours: report a time-out now
+        TL_CUDA(cudaStreamSynchronize(c->stream));
+        TL_TRY(tl_check_peer_timeout(c));
+    }
     return TL_OK;
 }
 

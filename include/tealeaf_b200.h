@@ -163,6 +163,8 @@ int tl_comms_destroy(tl_comms* k);
 int tl_comms_rank(const tl_comms* k);
 int tl_comms_size(const tl_comms* k);
 int tl_comms_barrier(tl_comms* k);                     /* barrier(),        comms.h:10 */
+int tl_comms_abort(tl_comms* k);                       /* abort_comms(),    comms.h:13 (MPI_Abort): the other ranks'
+                                                        * host-side waits fail with TL_ERR_COMMS at once */
 int tl_comms_sum(tl_comms* k, double* a);              /* sum_over_ranks,   comms.h:14; rank-ordered sum */
 int tl_comms_min(tl_comms* k, double* a);              /* min_over_ranks,   comms.h:15 */
 /* send_recv_message + wait_for_requests (comms.h:16-20) on HOST buffers: posts my message for
@@ -184,6 +186,14 @@ int tl_decompose(int grid_x_cells, int grid_y_cells, int num_chunks, int chunk,
 /* halo_update_driver (drivers/halo_update_driver.c:6-25): remote exchange (L/R then B/T, each
  * pack -> peer copy -> unpack) followed by the local reflective update. k may be NULL for one rank. */
 int tl_halo_update(tl_chunk* c, tl_comms* k, const int fields_to_exchange[6], int depth);
+
+/* Test hook: `reps` back-to-back halo exchanges with no host synchronisation in between, the field contents
+ * regenerated and every halo cell verified ON THE DEVICE each time (neighbour's cell or reflection at the edge of
+ * the grid_x_cells x grid_y_cells mesh, as remote_halo_driver.c:24-126 + local_halos.cpp produce them).
+ * *mismatches = number of wrong halo cells over all exchanges.  Environment TL_TEST_SKEW="rank:usec" delays that
+ * rank's host between the send and the unpack launches of every exchange phase. */
+int tl_halo_stress(tl_chunk* c, tl_comms* k, int grid_x_cells, int grid_y_cells, int reps, int depth,
+                   long* mismatches);
 
 /* ---- device-resident solver loops ---- */
 typedef struct {
@@ -216,6 +226,8 @@ typedef struct {
 } tl_solve_info;
 
 void tl_solve_opts_default(tl_solve_opts* o);
+/* 1 if the resident CG loop of this chunk runs the fused two-kernel iteration for the given fuse_p_into_w. */
+int tl_cg_loop_is_fused(const tl_chunk* c, int fuse_p_into_w);
 /* One timestep's linear solve: the body of solve() in diffuse.c:23-64 between the depth-2
  * halo update and solve_finished_driver, i.e. cg_driver / cheby_driver / ppcg_driver /
  * jacobi_driver with the same call order, iteration counts and results. */

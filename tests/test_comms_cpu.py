@@ -245,3 +245,40 @@ def test_message_length_mismatch_is_reported_and_session_is_reusable():
     for rank in (0, 1):
         for rep in (0, 1):
             assert "message length mismatch" in res[rank]["rep%d" % rep]
+
+
+def _abort_worker(rank, world, session, out):
+    import time
+    from exploringsycl_b200 import Comms, TeaLeafError
+    from exploringsycl_b200._lib import lib
+    comms = Comms(session, rank, world, host_only=True)
+    t0 = time.perf_counter()
+    if rank == 1:
+        time.sleep(0.3)
+        lib().tl_comms_abort(comms.handle)  # abort_comms(), comms.c:79-82, then the process exits without a barrier
+        out.put((rank, "aborted", 0.0))
+        return
+    try:
+        comms.barrier()  # rank 1 never arrives
+        out.put((rank, "no error", time.perf_counter() - t0))
+    except TeaLeafError as e:
+        out.put((rank, str(e), time.perf_counter() - t0))
+    # the peer is gone: no collective teardown
+
+
+def test_abort_poisons_the_segment_and_peers_fail_at_once():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    session = "pytest_abort_%d" % os.getpid()
+    procs = [ctx.Process(target=_abort_worker, args=(r, 2, session, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (msg, dt) for r, msg, dt in (out.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+    assert "peer rank aborted" in res[0][0], res
+    assert res[0][1] < 10.0  # not the 60 s time-out
+    try:  # nobody ran the collective teardown: remove the segment
+        os.unlink("/dev/shm/tl_b200_" + session)
+    except OSError:
+        pass

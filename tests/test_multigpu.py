@@ -44,7 +44,7 @@ def halo_worker(rank, world, session, grid, out):
     hd = 2
     ok = True
     for depth in (2, 1):
-        for rep in range(3):  # repeated exchanges exercise the parity double buffering
+        for rep in range(3):  # host-synchronised between exchanges; the back-to-back case is test_halo_exchange_stress
             jj, kk = np.meshgrid(np.arange(ch.y), np.arange(ch.x), indexing="ij")
             gxx, gyy = d["left"] + kk - hd, d["bottom"] + jj - hd
             truth = (gxx + 10000.0 * gyy + 0.25 * rep).astype(np.float64)
@@ -70,7 +70,29 @@ def halo_worker(rank, world, session, grid, out):
     comms.finalise()
 
 
-def deck_worker(rank, world, session, deck_file, over, out):
+def stress_worker(rank, world, session, grid, reps, skew, out):
+    """Back-to-back exchanges without host synchronisation, one rank's host delayed between send and unpack."""
+    import ctypes as C
+    if skew:
+        os.environ["TL_TEST_SKEW"] = skew
+    from exploringsycl_b200 import Chunk, Comms, decompose_field
+    from exploringsycl_b200._lib import check, lib
+    gx, gy = grid
+    comms = Comms(session, rank, world, device=rank)
+    d = decompose_field(gx, gy, world, rank)
+    ch = Chunk(d["nx"], d["ny"], 2, 10, d["neighbours"], d["left"], d["bottom"], device=rank)
+    check(lib().tl_comms_attach_chunk(comms.handle, ch.handle))
+    bad = C.c_long(-1)
+    check(lib().tl_halo_stress(ch.handle, comms.handle, gx, gy, reps, 2, C.byref(bad)))
+    out.put((rank, bad.value))
+    comms.barrier()
+    ch.close()
+    comms.finalise()
+
+
+def deck_worker(rank, world, session, deck_file, over, out, skew=None):
+    if skew:
+        os.environ["TL_TEST_SKEW"] = skew
     from exploringsycl_b200 import Comms, TeaLeaf, read_config
     comms = Comms(session, rank, world, device=rank)
     s, states = read_config(os.path.join(DECKS, deck_file))
@@ -88,7 +110,10 @@ def launch(target, world, args):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     session = "pytest_gpu_%d_%d" % (os.getpid(), free_port())
-    procs = [ctx.Process(target=target, args=(r, world, session) + args + (out,)) for r in range(world)]
+    extra = ()
+    if target is deck_worker and len(args) == 3:  # (deck, overrides, skew)
+        args, extra = args[:2], (args[2],)
+    procs = [ctx.Process(target=target, args=(r, world, session) + args + (out,) + extra) for r in range(world)]
     for p in procs:
         p.start()
     res = [out.get(timeout=600) for _ in range(world)]
@@ -105,6 +130,34 @@ def test_halo_exchange_bit_exact(world, grid):
         pytest.skip("needs %d GPUs" % world)
     for rank, ok in launch(halo_worker, world, (grid,)):
         assert ok, "rank %d halo mismatch" % rank
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("skew", [None, "0:300", "1:300"])
+def test_halo_exchange_stress(world, skew):
+    """200 exchanges (changing field sets, depths and contents, generated and verified on the device) with no host
+    synchronisation in between; with `skew` one rank's host sleeps 300 us between the send and the unpack launches
+    of every phase, so its neighbours run a full exchange ahead: a receive buffer reused before it was unpacked
+    (round-1 race: constant buffer parity per face, no ack) fails this test."""
+    if ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    for rank, bad in launch(stress_worker, world, ((96, 80), 200, skew)):
+        assert bad == 0, "rank %d: %d wrong halo cells" % (rank, bad)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("deck", ["tea_250_cheby.in", "tea_250_ppcg.in"])
+def test_cheby_ppcg_multi_rank_are_skew_invariant(world, deck):
+    """Chebyshev iterates up to 10 times and PPCG 10 inner steps with a halo exchange and no reduction in between:
+    a delayed rank must not change a single bit (advisor finding, round 1)."""
+    if ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    a = launch(deck_worker, world, (deck, {"end_step": 2}))
+    b = launch(deck_worker, world, (deck, {"end_step": 2}, "1:200"))
+    for (ra, sa, ha), (rb, sb, hb) in zip(a, b):
+        assert sa == sb
+        assert [(h["iters_a"], h["iters_b"], h["error"]) for h in ha] == \
+               [(h["iters_a"], h["iters_b"], h["error"]) for h in hb]
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
