@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtealeaf_b200.so")
-SOURCES = ["tl_kernels.cu", "tl_api.cu", "tl_solver.cu", "tl_comms.cu"]
+SOURCES = ["tl_kernels.cu", "tl_bulk.cu", "tl_api.cu", "tl_solver.cu", "tl_comms.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: every fp64 operation is rounded as the reference expression writes it (bit-exact
 # element-wise parity with the CPU oracle, which is built with -ffp-contract=off).

@@ -1,0 +1,314 @@
+// tl_device.cuh -- device-side helpers shared by the kernel translation units (tl_kernels.cu, tl_bulk.cu):
+// vector loads/stores, system-scope flag primitives of the NVLink paths, the deterministic single-pass grid
+// reduction, the reference SMVP association, the multi-rank slot/flag helpers and the hot-kernel tile geometry.
+#pragma once
+#include <utility>
+#include "tl_internal.h"
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The kernels of the resident CG loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: the CTAs of kernel N+1 become resident as the CTAs of kernel N
+// retire, run their prologue (barrier set-up, index arithmetic, loads of data that kernel N does not write) and block in
+// pdl_wait() until kernel N has completed and its writes are visible.  Every such kernel calls pdl_trigger() only AFTER
+// its own pdl_wait(), so when a kernel's CTAs run, everything older than its immediate predecessor is complete: data
+// written two launches ago may be read before the wait.  Without the launch attribute both calls are no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// kernel<<<grid, block, smem, stream>>>(args...) with the PDL attribute when `pdl` is set.
+// (Measured, profiles/pdl_r02.txt: forcing one shared-memory carve-out on all loop kernels so that their CTAs can share
+// SMs costs the register-staged kernels 15-30 %: with the L1 shrunk to its minimum they cannot keep enough loads in
+// flight.  The kernels therefore keep the driver's default carve-out.)
+template <class... KArgs, class... Args>
+static inline cudaError_t tl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ double2 ld2_ro(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
+__device__ __forceinline__ void st_pair(double* p, double2 v, bool v1)
+{
+    if (v1) st2(p, v);
+    else p[0] = v.x;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// system-scope flag primitives of the NVLink paths (halo exchange, resident multi-rank CG loop)
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_volatile_f64(const double* p)
+{
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU.  A timeout
+// is FATAL for the solve: the error mark goes to DevScal.pad and to the host-mapped error word, and the convergence stamp is
+// set so that every later launch of the resident loop returns at once; the host reports TL_ERR_COMMS at its next
+// synchronisation point (tl_check_peer_timeout).
+__device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
+                                          unsigned long long site = 0)
+{
+    const long long t0 = clock64();
+    unsigned long long seen;
+    while ((seen = ld_acquire_sys(flag)) < want) {
+        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
+        if (clock64() - t0 > 20000000000LL) { // ~10 s
+            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
+                S->dbg[0] = site;
+                S->dbg[1] = want;
+                S->dbg[2] = seen;
+                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
+                S->conv = 1;
+                S->conv_iter = 0; // mc_skip() is now true for every iteration: nothing computes on unknown data
+                if (S->err_host) *(volatile unsigned int*)S->err_host = 0xdeadu;
+                __threadfence_system();
+            }
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+// Loads of fields that change inside the solver loop (p, r, u, w).  ld.global.cg is served by L2, the point of
+// coherence both for NVLink peer stores (halo cells of p / r written by the neighbours while this kernel runs) and for the
+// preceding kernel of a programmatic dependent launch: with PDL this kernel's CTAs share SMs with the still-draining
+// predecessor and no launch boundary has invalidated L1, so the non-coherent path (ld.global.nc) or an L1 hit could
+// return a line from two launches ago.  The hot kernels therefore read those fields with COH = true; the constant
+// coefficient fields kx, ky keep the read-only path.
+template <bool COH>
+__device__ __forceinline__ double2 ldp2(const double* p)
+{
+    if constexpr (COH) return __ldcg(reinterpret_cast<const double2*>(p));
+    else return __ldg(reinterpret_cast<const double2*>(p));
+}
+template <bool COH>
+__device__ __forceinline__ double ldp1(const double* p)
+{
+    if constexpr (COH) return __ldcg(p);
+    else return __ldg(p);
+}
+struct RedArgs {
+    double* partials;   // [NR][cap]   one per tile
+    double* gpartials;  // [NR][gcap]  one per group of TL_RED_GROUP tiles
+    unsigned int* gcount; // [gcap]    arrival tickets per group (self-resetting)
+    int cap, gcap;
+    DevScal* S;
+};
+#define TL_RED_GROUP 64
+
+// Deterministic single-pass grid reduction, two levels.  Every CTA writes its NR tile partials.  Tiles
+// are grouped by index (64 per group): the last CTA of a group to arrive adds that group's partials in
+// a fixed order -- this happens while the rest of the grid is still streaming -- and the last group to
+// finish adds the group sums, again in a fixed order.  The serial tail after the last tile is therefore
+// ~ntiles/64 values instead of ntiles.  The result does not depend on arrival order.
+// Returns true in EVERY thread of the final CTA with the totals in `tot`.
+// CONSUMERS_ONLY: the CTA also holds a producer warp (tl_bulk.cu): only the first TL_TPB threads take part and
+// synchronise through named barrier 1 instead of __syncthreads().
+template <bool CONSUMERS_ONLY>
+__device__ __forceinline__ void red_sync()
+{
+    if constexpr (CONSUMERS_ONLY) asm volatile("bar.sync 1, %0;" ::"n"(TL_TPB) : "memory");
+    else __syncthreads();
+}
+template <int NR, bool CONSUMERS_ONLY = false>
+__device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
+                                            double (&tot)[NR])
+{
+    __shared__ double sm[NR][TL_TPB / 32];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int group = tile / TL_RED_GROUP;
+    const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
+    const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double v = warp_sum(acc[r]);
+        if (lane == 0) sm[r][wid] = v;
+    }
+    red_sync<CONSUMERS_ONLY>();
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            double v = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
+            __stcg(&ra.partials[(size_t)r * ra.cap + tile], v);
+        }
+        __threadfence();
+        s_flag = (atomicAdd(&ra.gcount[group], 1u) == (unsigned int)(gsize - 1));
+    }
+    red_sync<CONSUMERS_ONLY>();
+    if (!s_flag) return false;
+    // last CTA of this group: group sum (lanes of warps 0,1 hold one tile partial each)
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        double v = 0.0;
+        if (tid < gsize) v = __ldcg(ra.partials + (size_t)r * ra.cap + group * TL_RED_GROUP + tid);
+        v = warp_sum(v);
+        red_sync<CONSUMERS_ONLY>();
+        if (lane == 0) sm[r][wid] = v;
+    }
+    red_sync<CONSUMERS_ONLY>();
+    if (tid == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) __stcg(&ra.gpartials[(size_t)r * ra.gcap + group], sm[r][0] + sm[r][1]);
+        ra.gcount[group] = 0u;
+        __threadfence();
+        s_flag = (atomicAdd(&ra.S->counter[0], 1u) == (unsigned int)(ngroups - 1));
+    }
+    red_sync<CONSUMERS_ONLY>();
+    if (!s_flag) return false;
+    // last group: total
+    __threadfence();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const double* src = ra.gpartials + (size_t)r * ra.gcap;
+        double s = 0.0;
+#pragma unroll 4
+        for (int k = tid; k < ngroups; k += TL_TPB) s += __ldcg(src + k);
+        s = warp_sum(s);
+        red_sync<CONSUMERS_ONLY>();
+        if (lane == 0) sm[r][wid] = s;
+    }
+    red_sync<CONSUMERS_ONLY>();
+#pragma unroll
+    for (int r = 0; r < NR; ++r) tot[r] = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
+    if (tid == 0) ra.S->counter[0] = 0u;
+    return true;
+}
+
+// shared.h:59-63 -- the reference SMVP association, spelled out on registers:
+//   (1 + (kx[i+1]+kx[i]) + (ky[i+x]+ky[i]))*a[i] - (kx[i+1]*a[i+1]+kx[i]*a[i-1]) - (ky[i+x]*a[i+x]+ky[i]*a[i-x])
+__device__ __forceinline__ double smvp(double kx0, double kx1, double ky0, double ky1, double a,
+                                       double al, double ar, double ad, double au)
+{
+    return (1.0 + (kx1 + kx0) + (ky1 + ky0)) * a - (kx1 * ar + kx0 * al) - (ky1 * au + ky0 * ad);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Multi-rank helpers of the resident CG loop (see MultiCtx in tl_internal.h)
+// ---------------------------------------------------------------------------------------------
+// Sum of the N ranks' partials of (kind, local iteration tl) in rank order.  Called by ALL 32 lanes of
+// warp 0: lane r waits for rank r's flag and loads its partial (the N memory latencies overlap), then
+// the partials are added in rank order, identically on every rank (same order as tl_comms_sum).
+__device__ __forceinline__ double mc_sum_warp(const MultiCtx& mc, int kind, int tl, DevScal* S)
+{
+    const int lane = threadIdx.x & 31;
+    double v = 0.0;
+    if (lane < mc.num_ranks) {
+        const int idx = TL_SLOT_IDX(kind, tl & 1, lane);
+        spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
+                  1000ull + 100ull * kind + 10ull * lane + (unsigned long long)tl * 100000ull);
+        v = ld_volatile_f64(mc.slots_local + idx);
+    }
+    double s = __shfl_sync(0xffffffffu, v, 0);
+    for (int r = 1; r < mc.num_ranks; ++r) s = s + __shfl_sync(0xffffffffu, v, r);
+    return s;
+}
+// Tail of a reduction kernel, called by all lanes of warp 0 of the last CTA: lane r stores this rank's
+// partial into rank r's slot, fences, then releases rank r's flag.
+__device__ __forceinline__ void mc_publish_warp(const MultiCtx& mc, int kind, double partial)
+{
+    const int lane = threadIdx.x & 31;
+    if (lane < mc.num_ranks) {
+        const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
+        mc.slots_peer[lane][idx] = partial;
+        __threadfence_system();
+        st_release_sys(mc.sflags_peer[lane] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
+    }
+}
+__device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
+{
+    return S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
+}
+// Head of every multi-rank kernel: is this launch a no-op?  Once calc_p of iteration X has seen
+// convergence it stamps conv_iter = X + 1; every later launch returns at once.  (One HBM-resident
+// scalar written in an earlier kernel: no peer traffic, no slot reads on this path.)
+__device__ __forceinline__ bool mc_skip(const MultiCtx& mc, const DevScal* S)
+{
+    return mc.it_global >= *(volatile const int*)&S->conv_iter;
+}
+
+// Hot-kernel tile: TL_TPB threads x 2 columns, `rows` rows.  kk is the first of the thread's two
+// columns; (off + kk) is even by construction, so double2 accesses are 16-byte aligned and a warp
+// covers 512 contiguous, 128-byte-aligned bytes of a row.
+struct HotTile {
+    int kk, j0, j1, tile, ntiles;
+    bool v0, v1;
+    long i;
+};
+__device__ __forceinline__ HotTile hot_tile(const Geo& g, int rows, int rev)
+{
+    HotTile t;
+    const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
+    const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+    t.kk = g.hd + 2 * (bx * TL_TPB + threadIdx.x);
+    t.v0 = t.kk < g.x - g.hd;
+    t.v1 = t.kk + 1 < g.x - g.hd;
+    t.j0 = g.hd + by * rows;
+    t.j1 = min(t.j0 + rows, g.y - g.hd);
+    t.i = (long)g.off + (long)t.j0 * g.pitch + t.kk;
+    t.tile = by * gridDim.x + bx;
+    t.ntiles = gridDim.x * gridDim.y;
+    return t;
+}
+
+// Multi-rank: the thread that owns an edge cell of an INTERNAL face stores the updated p straight into
+// the neighbour's halo cell over NVLink (what pack -> MPI -> unpack does in remote_halo_driver.c for
+// depth 1; the 5-point stencil never reads halo corners, so none are sent).
+__device__ __forceinline__ void edge_remote_store(const Geo& g, const MultiCtx& mc, double* const* nbf, int jj,
+                                                  double2 pv, const HotTile& t)
+{
+    const int last = g.x - g.hd - 1;
+    if (nbf[TL_FACE_LEFT] && t.kk == g.hd) // my first column -> left neighbour's right halo column
+        nbf[TL_FACE_LEFT][(long)mc.nb_off[TL_FACE_LEFT] + (long)jj * mc.nb_pitch[TL_FACE_LEFT] +
+                              (mc.nb_x[TL_FACE_LEFT] - g.hd)] = pv.x;
+    if (nbf[TL_FACE_RIGHT]) { // my last column -> right neighbour's left halo column
+        double* q = nbf[TL_FACE_RIGHT] + (long)mc.nb_off[TL_FACE_RIGHT] + (long)jj * mc.nb_pitch[TL_FACE_RIGHT] +
+                    (g.hd - 1);
+        if (t.kk == last) *q = pv.x;
+        else if (t.kk + 1 == last) *q = pv.y;
+    }
+    if (nbf[TL_FACE_BOTTOM] && jj == g.hd) { // my first row -> bottom neighbour's top halo row
+        double* q = nbf[TL_FACE_BOTTOM] + (long)mc.nb_off[TL_FACE_BOTTOM] +
+                    (long)(mc.nb_y[TL_FACE_BOTTOM] - g.hd) * mc.nb_pitch[TL_FACE_BOTTOM] + t.kk;
+        st_pair(q, pv, t.v1);
+    }
+    if (nbf[TL_FACE_TOP] && jj == g.y - g.hd - 1) { // my last row -> top neighbour's bottom halo row
+        double* q = nbf[TL_FACE_TOP] + (long)mc.nb_off[TL_FACE_TOP] + (long)(g.hd - 1) * mc.nb_pitch[TL_FACE_TOP] +
+                    t.kk;
+        st_pair(q, pv, t.v1);
+    }
+}
+

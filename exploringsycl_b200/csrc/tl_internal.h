@@ -151,10 +151,10 @@ int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, c
                        unsigned long long* const flags[2], unsigned long long* const acks[2],
                        const unsigned long long seqs[2]);
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal->sums[0] (rro part)
-int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr);                // -> scal->pw (& alpha when SCAL_DEV)
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false); // -> scal->rrn (& beta, conv when SCAL_DEV)
-int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc = nullptr);
-int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc = nullptr);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr, bool pdl = false);                // -> scal->pw (& alpha when SCAL_DEV)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false, bool pdl = false); // -> scal->rrn (& beta, conv when SCAL_DEV)
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc = nullptr, bool pdl = false);
+int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc = nullptr, bool pdl = false);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
 int tlk_cheby_calc_u(tl_chunk* c);
@@ -171,6 +171,17 @@ int tlk_calculate_2norm(tl_chunk* c, int field);          // -> scal->sums[0]
 int tlk_finalise(tl_chunk* c);
 int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters);
 int tlk_seed_rro(tl_chunk* c);                            // scal->rro = scal->sums[0] (after cg_init)
+
+// tile geometry / tuning of the hot kernels (tl_kernels.cu), shared with tl_bulk.cu
+enum { TUNE_W = 0, TUNE_UR = 1, TUNE_P = 2, TUNE_PW = 3 };
+int tlk_tile_rows(const tl_chunk* c, int kernel);
+dim3 tlk_hot_grid(const tl_chunk* c, int rows);
+int tlk_hot_check(const tl_chunk* c, dim3 grid);
+int tlk_external_mask(const tl_chunk* c);
+extern const MultiCtx g_single_ctx;
+// tl_bulk.cu: the fused p-update + matvec kernel on a cp.async.bulk shared-memory row pipeline
+bool tlk_pw_uses_bulk();
+int tlk_cg_calc_pw_bulk(tl_chunk* c, bool rev, const MultiCtx* mc, int rows, bool pdl);
 
 // fetch the DevScal to the pinned mirror and wait
 int tl_fetch_scal(tl_chunk* c);

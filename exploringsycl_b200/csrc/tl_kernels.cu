@@ -12,175 +12,9 @@
 // and the minimum number of passes over HBM.  Tensor cores / TMEM are not used.
 #include <stdlib.h>
 #include "tl_internal.h"
+#include "tl_device.cuh"
 
 long g_tl_launches = 0;
-
-// ---------------------------------------------------------------------------------------------
-// small device helpers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
-__device__ __forceinline__ double2 ld2_ro(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
-__device__ __forceinline__ void st2(double* p, double2 v) { *reinterpret_cast<double2*>(p) = v; }
-__device__ __forceinline__ void st_pair(double* p, double2 v, bool v1)
-{
-    if (v1) st2(p, v);
-    else p[0] = v.x;
-}
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// system-scope flag primitives of the NVLink paths (halo exchange, resident multi-rank CG loop)
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ double ld_volatile_f64(const double* p)
-{
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-// Spin until *flag >= want.  Bounded (~10 s; later waits bail at once) so that a lost peer cannot hang the GPU.  A timeout
-// is FATAL for the solve: the error mark goes to DevScal.pad and to the host-mapped error word, and the convergence stamp is
-// set so that every later launch of the resident loop returns at once; the host reports TL_ERR_COMMS at its next
-// synchronisation point (tl_check_peer_timeout).
-__device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsigned long long want, DevScal* S,
-                                          unsigned long long site = 0)
-{
-    const long long t0 = clock64();
-    unsigned long long seen;
-    while ((seen = ld_acquire_sys(flag)) < want) {
-        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
-        if (clock64() - t0 > 20000000000LL) { // ~10 s
-            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
-                S->dbg[0] = site;
-                S->dbg[1] = want;
-                S->dbg[2] = seen;
-                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
-                S->conv = 1;
-                S->conv_iter = 0; // mc_skip() is now true for every iteration: nothing computes on unknown data
-                if (S->err_host) *(volatile unsigned int*)S->err_host = 0xdeadu;
-                __threadfence_system();
-            }
-            break;
-        }
-        __nanosleep(64);
-    }
-}
-// Loads of data that a peer GPU may store while this kernel runs (halo cells of p / r in the multi-rank loop): ld.global.cg
-// is served by L2, the point of coherence for NVLink peer stores; the non-coherent path (ld.global.nc / L1) could return a
-// sector fetched before the neighbour's flag arrived.  Single-rank instantiations keep the read-only path.
-template <bool COH>
-__device__ __forceinline__ double2 ldp2(const double* p)
-{
-    if constexpr (COH) return __ldcg(reinterpret_cast<const double2*>(p));
-    else return __ldg(reinterpret_cast<const double2*>(p));
-}
-template <bool COH>
-__device__ __forceinline__ double ldp1(const double* p)
-{
-    if constexpr (COH) return __ldcg(p);
-    else return __ldg(p);
-}
-struct RedArgs {
-    double* partials;   // [NR][cap]   one per tile
-    double* gpartials;  // [NR][gcap]  one per group of TL_RED_GROUP tiles
-    unsigned int* gcount; // [gcap]    arrival tickets per group (self-resetting)
-    int cap, gcap;
-    DevScal* S;
-};
-#define TL_RED_GROUP 64
-
-// Deterministic single-pass grid reduction, two levels.  Every CTA writes its NR tile partials.  Tiles
-// are grouped by index (64 per group): the last CTA of a group to arrive adds that group's partials in
-// a fixed order -- this happens while the rest of the grid is still streaming -- and the last group to
-// finish adds the group sums, again in a fixed order.  The serial tail after the last tile is therefore
-// ~ntiles/64 values instead of ntiles.  The result does not depend on arrival order.
-// Returns true in EVERY thread of the final CTA with the totals in `tot`.
-template <int NR>
-__device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
-                                            double (&tot)[NR])
-{
-    __shared__ double sm[NR][TL_TPB / 32];
-    __shared__ int s_flag;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int group = tile / TL_RED_GROUP;
-    const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
-    const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        double v = warp_sum(acc[r]);
-        if (lane == 0) sm[r][wid] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            double v = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
-            __stcg(&ra.partials[(size_t)r * ra.cap + tile], v);
-        }
-        __threadfence();
-        s_flag = (atomicAdd(&ra.gcount[group], 1u) == (unsigned int)(gsize - 1));
-    }
-    __syncthreads();
-    if (!s_flag) return false;
-    // last CTA of this group: group sum (lanes of warps 0,1 hold one tile partial each)
-    __threadfence();
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        double v = 0.0;
-        if (tid < gsize) v = __ldcg(ra.partials + (size_t)r * ra.cap + group * TL_RED_GROUP + tid);
-        v = warp_sum(v);
-        __syncthreads();
-        if (lane == 0) sm[r][wid] = v;
-    }
-    __syncthreads();
-    if (tid == 0) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) __stcg(&ra.gpartials[(size_t)r * ra.gcap + group], sm[r][0] + sm[r][1]);
-        ra.gcount[group] = 0u;
-        __threadfence();
-        s_flag = (atomicAdd(&ra.S->counter[0], 1u) == (unsigned int)(ngroups - 1));
-    }
-    __syncthreads();
-    if (!s_flag) return false;
-    // last group: total
-    __threadfence();
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        const double* src = ra.gpartials + (size_t)r * ra.gcap;
-        double s = 0.0;
-#pragma unroll 4
-        for (int k = tid; k < ngroups; k += TL_TPB) s += __ldcg(src + k);
-        s = warp_sum(s);
-        __syncthreads();
-        if (lane == 0) sm[r][wid] = s;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < NR; ++r) tot[r] = (sm[r][0] + sm[r][1]) + (sm[r][2] + sm[r][3]);
-    if (tid == 0) ra.S->counter[0] = 0u;
-    return true;
-}
-
-// shared.h:59-63 -- the reference SMVP association, spelled out on registers:
-//   (1 + (kx[i+1]+kx[i]) + (ky[i+x]+ky[i]))*a[i] - (kx[i+1]*a[i+1]+kx[i]*a[i-1]) - (ky[i+x]*a[i+x]+ky[i]*a[i-x])
-__device__ __forceinline__ double smvp(double kx0, double kx1, double ky0, double ky1, double a,
-                                       double al, double ar, double ad, double au)
-{
-    return (1.0 + (kx1 + kx0) + (ky1 + ky0)) * a - (kx1 * ar + kx0 * al) - (ky1 * au + ky0 * ad);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Generic row-tiled kernel: one thread per column, `rows` rows per CTA, optional NR-wide reduction.
@@ -650,107 +484,10 @@ int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
     return TL_OK;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Multi-rank helpers of the resident CG loop (see MultiCtx in tl_internal.h)
-// ---------------------------------------------------------------------------------------------
-// Sum of the N ranks' partials of (kind, local iteration tl) in rank order.  Called by ALL 32 lanes of
-// warp 0: lane r waits for rank r's flag and loads its partial (the N memory latencies overlap), then
-// the partials are added in rank order, identically on every rank (same order as tl_comms_sum).
-__device__ __forceinline__ double mc_sum_warp(const MultiCtx& mc, int kind, int tl, DevScal* S)
-{
-    const int lane = threadIdx.x & 31;
-    double v = 0.0;
-    if (lane < mc.num_ranks) {
-        const int idx = TL_SLOT_IDX(kind, tl & 1, lane);
-        spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
-                  1000ull + 100ull * kind + 10ull * lane + (unsigned long long)tl * 100000ull);
-        v = ld_volatile_f64(mc.slots_local + idx);
-    }
-    double s = __shfl_sync(0xffffffffu, v, 0);
-    for (int r = 1; r < mc.num_ranks; ++r) s = s + __shfl_sync(0xffffffffu, v, r);
-    return s;
-}
-// Tail of a reduction kernel, called by all lanes of warp 0 of the last CTA: lane r stores this rank's
-// partial into rank r's slot, fences, then releases rank r's flag.
-__device__ __forceinline__ void mc_publish_warp(const MultiCtx& mc, int kind, double partial)
-{
-    const int lane = threadIdx.x & 31;
-    if (lane < mc.num_ranks) {
-        const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
-        mc.slots_peer[lane][idx] = partial;
-        __threadfence_system();
-        st_release_sys(mc.sflags_peer[lane] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
-    }
-}
-__device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
-{
-    return S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
-}
-// Head of every multi-rank kernel: is this launch a no-op?  Once calc_p of iteration X has seen
-// convergence it stamps conv_iter = X + 1; every later launch returns at once.  (One HBM-resident
-// scalar written in an earlier kernel: no peer traffic, no slot reads on this path.)
-__device__ __forceinline__ bool mc_skip(const MultiCtx& mc, const DevScal* S)
-{
-    return mc.it_global >= *(volatile const int*)&S->conv_iter;
-}
-
-// Hot-kernel tile: TL_TPB threads x 2 columns, `rows` rows.  kk is the first of the thread's two
-// columns; (off + kk) is even by construction, so double2 accesses are 16-byte aligned and a warp
-// covers 512 contiguous, 128-byte-aligned bytes of a row.
-struct HotTile {
-    int kk, j0, j1, tile, ntiles;
-    bool v0, v1;
-    long i;
-};
-__device__ __forceinline__ HotTile hot_tile(const Geo& g, int rows, int rev)
-{
-    HotTile t;
-    const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-    const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-    t.kk = g.hd + 2 * (bx * TL_TPB + threadIdx.x);
-    t.v0 = t.kk < g.x - g.hd;
-    t.v1 = t.kk + 1 < g.x - g.hd;
-    t.j0 = g.hd + by * rows;
-    t.j1 = min(t.j0 + rows, g.y - g.hd);
-    t.i = (long)g.off + (long)t.j0 * g.pitch + t.kk;
-    t.tile = by * gridDim.x + bx;
-    t.ntiles = gridDim.x * gridDim.y;
-    return t;
-}
-
-// Multi-rank: the thread that owns an edge cell of an INTERNAL face stores the updated p straight into
-// the neighbour's halo cell over NVLink (what pack -> MPI -> unpack does in remote_halo_driver.c for
-// depth 1; the 5-point stencil never reads halo corners, so none are sent).
-__device__ __forceinline__ void edge_remote_store(const Geo& g, const MultiCtx& mc, double* const* nbf, int jj,
-                                                  double2 pv, const HotTile& t)
-{
-    const int last = g.x - g.hd - 1;
-    if (nbf[TL_FACE_LEFT] && t.kk == g.hd) // my first column -> left neighbour's right halo column
-        nbf[TL_FACE_LEFT][(long)mc.nb_off[TL_FACE_LEFT] + (long)jj * mc.nb_pitch[TL_FACE_LEFT] +
-                              (mc.nb_x[TL_FACE_LEFT] - g.hd)] = pv.x;
-    if (nbf[TL_FACE_RIGHT]) { // my last column -> right neighbour's left halo column
-        double* q = nbf[TL_FACE_RIGHT] + (long)mc.nb_off[TL_FACE_RIGHT] + (long)jj * mc.nb_pitch[TL_FACE_RIGHT] +
-                    (g.hd - 1);
-        if (t.kk == last) *q = pv.x;
-        else if (t.kk + 1 == last) *q = pv.y;
-    }
-    if (nbf[TL_FACE_BOTTOM] && jj == g.hd) { // my first row -> bottom neighbour's top halo row
-        double* q = nbf[TL_FACE_BOTTOM] + (long)mc.nb_off[TL_FACE_BOTTOM] +
-                    (long)(mc.nb_y[TL_FACE_BOTTOM] - g.hd) * mc.nb_pitch[TL_FACE_BOTTOM] + t.kk;
-        st_pair(q, pv, t.v1);
-    }
-    if (nbf[TL_FACE_TOP] && jj == g.y - g.hd - 1) { // my last row -> top neighbour's bottom halo row
-        double* q = nbf[TL_FACE_TOP] + (long)mc.nb_off[TL_FACE_TOP] + (long)(g.hd - 1) * mc.nb_pitch[TL_FACE_TOP] +
-                    t.kk;
-        st_pair(q, pv, t.v1);
-    }
-}
-
 // Tuning knobs (tl_set_tuning): rows per tile and rows per load batch for each hot kernel family.
 // The load batch U is the number of rows whose loads are issued back to back before any of them is
 // consumed: it sets the bytes each thread keeps in flight (the kernels are latency-bound, not
 // issue-bound; see DESIGN.md "in-flight bytes").
-enum { TUNE_W = 0, TUNE_UR = 1, TUNE_P = 2, TUNE_PW = 3 };
 // rows == 0 selects the built-in heuristic (tile_rows).  Defaults from the round-1 sweep on B200
 // (profiles/tuning_r01.txt): stencil kernels want tall tiles (the two extra rows of p per tile are
 // re-read from L2), the streaming kernels want many small tiles (better tail balance).
@@ -782,7 +519,7 @@ static void tune_from_env()
     }
 }
 
-static int tile_rows(const tl_chunk* c, int kernel)
+int tlk_tile_rows(const tl_chunk* c, int kernel)
 {
     tune_from_env();
     if (g_rows[kernel] > 0) return g_rows[kernel];
@@ -798,11 +535,11 @@ static int tile_rows(const tl_chunk* c, int kernel)
     if (rows > 128) rows = 128;
     return rows;
 }
-static dim3 hot_grid(const tl_chunk* c, int rows)
+dim3 tlk_hot_grid(const tl_chunk* c, int rows)
 {
     return dim3((c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS, (c->ny + rows - 1) / rows);
 }
-static int hot_check(const tl_chunk* c, dim3 grid)
+int tlk_hot_check(const tl_chunk* c, dim3 grid)
 {
     if ((long)grid.x * grid.y > c->partial_cap) {
         tl_set_error("partials capacity exceeded");
@@ -822,6 +559,8 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
 {
     DevScal* S = ra.S;
     constexpr bool multi = MULTI;
+    pdl_wait(); // p (and the solver scalars) come from the preceding kernels
+    pdl_trigger();
     if (mode == SCAL_DEV && !multi) {
         const int conv = S->conv;
         if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S->p_pending = 0;
@@ -853,9 +592,9 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
     if (t.v0) {
         long i = t.i;
         const long pitch = g.pitch;
-        double2 pm = ldp2<MULTI>(p + i - pitch);
-        double2 pc = ldp2<MULTI>(p + i);
-        double pl = ldp1<MULTI>(p + i - 1), pr = ldp1<MULTI>(p + i + 2);
+        double2 pm = ldp2<true>(p + i - pitch);
+        double2 pc = ldp2<true>(p + i);
+        double pl = ldp1<true>(p + i - 1), pr = ldp1<true>(p + i + 2);
         double2 kyc = ld2_ro(ky + i);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             double2 pn[U], kyn[U], kxc[U];
@@ -864,12 +603,12 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
             for (int u = 0; u < U; ++u) {
                 if (jb + u < t.j1) {
                     const long iu = i + u * pitch;
-                    pn[u] = ldp2<MULTI>(p + iu + pitch);
+                    pn[u] = ldp2<true>(p + iu + pitch);
                     kyn[u] = ld2_ro(ky + iu + pitch);
                     kxc[u] = ld2_ro(kx + iu);
                     kxr[u] = __ldg(kx + iu + 2);
-                    pln[u] = ldp1<MULTI>(p + iu + pitch - 1);
-                    prn[u] = ldp1<MULTI>(p + iu + pitch + 2);
+                    pln[u] = ldp1<true>(p + iu + pitch - 1);
+                    prn[u] = ldp1<true>(p + iu + pitch + 2);
                 }
             }
 #pragma unroll
@@ -902,23 +641,23 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
     }
 }
 
-static const MultiCtx g_single_ctx = {1};
+const MultiCtx g_single_ctx = {1};
 
-int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc)
+int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc, bool pdl)
 {
-    const int rows = tile_rows(c, TUNE_W);
-    dim3 grid = hot_grid(c, rows);
-    TL_TRY(hot_check(c, grid));
+    const int rows = tlk_tile_rows(c, TUNE_W);
+    dim3 grid = tlk_hot_grid(c, rows);
+    TL_TRY(tlk_hot_check(c, grid));
     RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
 #define LAUNCH_W(U)                                                                                          \
     if (mc && mc->num_ranks > 1)                                                                             \
-        k_cg_calc_w<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],          \
-                                                            c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, \
-                                                            (int)mode, rows, rev ? 1 : 0, *mc);                  \
+        TL_CUDA(tl_launch(k_cg_calc_w<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],   \
+                          c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, (int)mode,    \
+                          rows, rev ? 1 : 0, *mc));                                                            \
     else                                                                                                     \
-        k_cg_calc_w<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_KX],         \
-                                                             c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, \
-                                                             (int)mode, rows, rev ? 1 : 0, g_single_ctx)
+        TL_CUDA(tl_launch(k_cg_calc_w<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],  \
+                          c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W], c->d_alphas, ra, (int)mode,    \
+                          rows, rev ? 1 : 0, g_single_ctx))
     switch (g_batch[TUNE_W]) {
     case 1: LAUNCH_W(1); break;
     case 2: LAUNCH_W(2); break;
@@ -934,38 +673,52 @@ int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc)
 // 48 B/cell: read u, p, r, w; write u, r.
 template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
-k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double* __restrict__ p,
-             const double* __restrict__ w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
+k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, double* __restrict__ d_betas, RedArgs ra, int mode, double alpha_imm,
              int rows, int rev, double* __restrict__ d_alphas, const MultiCtx mc, int send_r_halo)
 {
     DevScal* S = ra.S;
     constexpr bool multi = MULTI;
     double alpha = alpha_imm;
-    if (mode == SCAL_DEV && !multi) {
-        if (S->conv) return;
-        alpha = S->alpha;
-    }
     const HotTile t = hot_tile(g, rows, rev);
     const long pitch = g.pitch;
     double acc[1] = {0.0};
     long i = t.i;
     double2 uv[U], rv[U], pv[U], wv[U];
-    auto load_batch = [&](int jb) {
+    auto load_ur = [&](int jb) { // u, r: last written by the previous calc_ur (or cg_init), two launches back
 #pragma unroll
         for (int q = 0; q < U; ++q) {
             if (jb + q < t.j1) {
-                const long iq = i + q * pitch;
-                uv[q] = ld2(u + iq);
-                rv[q] = ld2(r + iq);
-                pv[q] = ld2_ro(p + iq);
-                wv[q] = ld2_ro(w + iq);
+                uv[q] = ldp2<true>(u + i + q * pitch);
+                rv[q] = ldp2<true>(r + i + q * pitch);
             }
         }
     };
+    auto load_pw = [&](int jb) { // p, w: written by the kernel just before this one
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (jb + q < t.j1) {
+                pv[q] = ldp2<true>(p + i + q * pitch);
+                wv[q] = ldp2<true>(w + i + q * pitch);
+            }
+        }
+    };
+    auto load_batch = [&](int jb) {
+        load_ur(jb);
+        load_pw(jb);
+    };
+    // Programmatic dependent launch: this CTA may be resident while the preceding matvec kernel is still draining;
+    // the first rows of u and r are requested before the wait, p and w after it.
+    if (t.v0) load_ur(t.j0);
+    pdl_wait();
+    pdl_trigger();
+    if (mode == SCAL_DEV && !multi) {
+        if (S->conv) return;
+        alpha = S->alpha;
+    }
+    if (t.v0) load_pw(t.j0);
     // The first batch of loads does not depend on alpha: it is issued BEFORE the multi-rank head, so the
     // wait for the peers' p.w partials overlaps with this tile's HBM latency.
     if constexpr (MULTI) {
-        if (t.v0) load_batch(t.j0);
         __shared__ int s_skip;
         __shared__ double s_alpha;
         if (threadIdx.x < 32) {
@@ -990,7 +743,7 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
     }
     if (t.v0) {
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-            if (!MULTI || jb != t.j0) load_batch(jb);
+            if (jb != t.j0) load_batch(jb);
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 if (jb + q < t.j1) {
@@ -1042,23 +795,21 @@ k_cg_calc_ur(Geo g, double* __restrict__ u, double* __restrict__ r, const double
     }
 }
 
-int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc, bool send_r_halo)
+int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc, bool send_r_halo, bool pdl)
 {
-    const int rows = tile_rows(c, TUNE_UR);
-    dim3 grid = hot_grid(c, rows);
-    TL_TRY(hot_check(c, grid));
+    const int rows = tlk_tile_rows(c, TUNE_UR);
+    dim3 grid = tlk_hot_grid(c, rows);
+    TL_TRY(tlk_hot_check(c, grid));
     RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
 #define LAUNCH_UR(U)                                                                                       \
     if (mc && mc->num_ranks > 1)                                                                           \
-        k_cg_calc_ur<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],        \
-                                                             c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra, \
-                                                             (int)mode, alpha, rows, rev ? 1 : 0, c->d_alphas, \
-                                                             *mc, send_r_halo ? 1 : 0);                        \
+        TL_CUDA(tl_launch(k_cg_calc_ur<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_U], \
+                          c->f[TL_FIELD_R], c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas, ra, (int)mode,      \
+                          alpha, rows, rev ? 1 : 0, c->d_alphas, *mc, send_r_halo ? 1 : 0));                  \
     else                                                                                                   \
-        k_cg_calc_ur<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_U], c->f[TL_FIELD_R],       \
-                                                              c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas,  \
-                                                              ra, (int)mode, alpha, rows, rev ? 1 : 0,          \
-                                                              c->d_alphas, g_single_ctx, 0)
+        TL_CUDA(tl_launch(k_cg_calc_ur<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g,                 \
+                          c->f[TL_FIELD_U], c->f[TL_FIELD_R], c->f[TL_FIELD_P], c->f[TL_FIELD_W], c->d_betas,  \
+                          ra, (int)mode, alpha, rows, rev ? 1 : 0, c->d_alphas, g_single_ctx, 0))
     switch (g_batch[TUNE_UR]) {
     case 1: LAUNCH_UR(1); break;
     case 2: LAUNCH_UR(2); break;
@@ -1101,31 +852,39 @@ __device__ __forceinline__ void p_halo_store(const Geo& g, double* p, long i, in
 // the external faces in the mask, so the resident loop needs no separate halo launches.
 template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
-k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal* S, int mode, double beta_imm,
+k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta_imm,
             int rows, int rev, int halo_mask, double* __restrict__ d_betas, const MultiCtx mc)
 {
     constexpr bool multi = MULTI;
     double beta = beta_imm;
+    const HotTile t = hot_tile(g, rows, rev);
+    const long pitch = g.pitch;
+    long i = t.i;
+    double2 pv[U], rv[U];
+    auto load_p = [&](int jb) { // p: last written by the previous calc_p / calc_pw, at least two launches back
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (jb + q < t.j1) pv[q] = ldp2<true>(p + i + q * pitch);
+    };
+    auto load_r = [&](int jb) { // r: written by the calc_ur just before this kernel
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (jb + q < t.j1) rv[q] = ldp2<true>(r + i + q * pitch);
+    };
+    auto load_batch = [&](int jb) {
+        load_p(jb);
+        load_r(jb);
+    };
+    if (t.v0) load_p(t.j0); // programmatic dependent launch: requested while calc_ur may still be draining
+    pdl_wait();
+    pdl_trigger();
     if (mode == SCAL_DEV && !multi) {
         if (!S->p_pending) return;
         beta = S->beta;
     }
-    const HotTile t = hot_tile(g, rows, rev);
     if (!MULTI && !t.v0) return;
-    const long pitch = g.pitch;
-    long i = t.i;
-    double2 pv[U], rv[U];
-    auto load_batch = [&](int jb) {
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (jb + q < t.j1) {
-                pv[q] = ld2(p + i + q * pitch);
-                rv[q] = ld2_ro(r + i + q * pitch);
-            }
-        }
-    };
+    if (t.v0) load_r(t.j0); // before the multi-rank head: overlaps the wait for the peers' r.r partials
     if constexpr (MULTI) {
-        if (t.v0) load_batch(t.j0); // before the head: overlaps the wait for the peers' r.r partials
         __shared__ int s_skip;
         __shared__ double s_beta;
         if (threadIdx.x < 32) {
@@ -1158,7 +917,7 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
         const bool edge_tile = (halo_mask || multi) && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
                                                         blockIdx.x == gridDim.x - 1);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-            if (!MULTI || jb != t.j0) load_batch(jb);
+            if (jb != t.j0) load_batch(jb);
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 if (jb + q < t.j1) {
@@ -1197,7 +956,7 @@ k_cg_calc_p(Geo g, double* __restrict__ p, const double* __restrict__ r, DevScal
     }
 }
 
-static int external_mask(const tl_chunk* c)
+int tlk_external_mask(const tl_chunk* c)
 {
     int mask = 0;
     if (c->nb[TL_FACE_LEFT] == TL_EXTERNAL_FACE) mask |= 1;
@@ -1207,20 +966,20 @@ static int external_mask(const tl_chunk* c)
     return mask;
 }
 
-int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc)
+int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc, bool pdl)
 {
-    const int rows = tile_rows(c, TUNE_P);
-    dim3 grid = hot_grid(c, rows);
-    const int mask = fuse_halo ? external_mask(c) : 0;
+    const int rows = tlk_tile_rows(c, TUNE_P);
+    dim3 grid = tlk_hot_grid(c, rows);
+    const int mask = fuse_halo ? tlk_external_mask(c) : 0;
 #define LAUNCH_P(U)                                                                                         \
     if (mc && mc->num_ranks > 1)                                                                            \
-        k_cg_calc_p<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R], c->scal, \
-                                                            (int)mode, beta, rows, rev ? 1 : 0, mask,          \
-                                                            c->d_betas, *mc);                                  \
+        TL_CUDA(tl_launch(k_cg_calc_p<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],  \
+                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->d_betas,      \
+                          *mc));                                                                              \
     else                                                                                                    \
-        k_cg_calc_p<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->f[TL_FIELD_R],        \
-                                                             c->scal, (int)mode, beta, rows, rev ? 1 : 0,      \
-                                                             mask, c->d_betas, g_single_ctx)
+        TL_CUDA(tl_launch(k_cg_calc_p<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P], \
+                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->d_betas,      \
+                          g_single_ctx))
     switch (g_batch[TUNE_P]) {
     case 1: LAUNCH_P(1); break;
     case 2: LAUNCH_P(2); break;
@@ -1251,6 +1010,8 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
 {
     DevScal* S = ra.S;
     double beta;
+    pdl_wait(); // r comes from the calc_ur just before this kernel; w may not be overwritten while it still reads it
+    pdl_trigger();
     if constexpr (!MULTI) {
         if (S->conv) return;
         beta = S->beta;
@@ -1313,13 +1074,13 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
     const bool halo_l = MULTI && t.v0 && !(ext_mask & 1) && t.kk == klo;
     const bool halo_r = MULTI && !(ext_mask & 2) && ((t.v1 && t.kk + 1 == khi) || (t.v0 && !t.v1 && t.kk == khi));
     auto pnew2 = [&](long i) {
-        double2 a = ldp2<MULTI>(p_in + i);
-        const double2 b = ldp2<MULTI>(r + i);
+        double2 a = ldp2<true>(p_in + i);
+        const double2 b = ldp2<true>(r + i);
         a.x = beta * a.x + b.x;
         a.y = beta * a.y + b.y;
         return a;
     };
-    auto pnew1 = [&](long i) { return beta * ldp1<MULTI>(p_in + i) + ldp1<MULTI>(r + i); };
+    auto pnew1 = [&](long i) { return beta * ldp1<true>(p_in + i) + ldp1<true>(r + i); };
     // sides of an updated row held as double2 `c` in every lane
     auto sides = [&](double2 c, long i, double& l, double& rr) {
         const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);
@@ -1403,29 +1164,34 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
 }
 
 // p_in = c->f[P], p_out = c->p2; the caller swaps them after the launch.
-int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc)
+int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
 {
-    const int rows = tile_rows(c, TUNE_PW);
-    dim3 grid = hot_grid(c, rows);
-    TL_TRY(hot_check(c, grid));
+    const int rows = tlk_tile_rows(c, TUNE_PW);
+    dim3 grid = tlk_hot_grid(c, rows);
+    TL_TRY(tlk_hot_check(c, grid));
     if (!c->p2) {
         TL_CUDA(cudaMalloc((void**)&c->p2, c->field_elems * sizeof(double)));
         c->p2_alloc = c->p2;
         TL_CUDA(cudaMemsetAsync(c->p2, 0, c->field_elems * sizeof(double), c->stream));
     }
+    if (tlk_pw_uses_bulk()) { // optional: TMA bulk-copy row pipeline, persistent CTAs (tl_bulk.cu); bit-identical results
+        TL_TRY(tlk_cg_calc_pw_bulk(c, rev, mc, rows, pdl));
+        double* tmp = c->f[TL_FIELD_P];
+        c->f[TL_FIELD_P] = c->p2;
+        c->p2 = tmp;
+        return TL_OK;
+    }
     RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
-    const int mask = external_mask(c);
+    const int mask = tlk_external_mask(c);
 #define LAUNCH_PW(U)                                                                                          \
     if (mc && mc->num_ranks > 1)                                                                              \
-        k_cg_calc_pw<U, true><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],    \
-                                                             c->f[TL_FIELD_KX], c->f[TL_FIELD_KY],               \
-                                                             c->f[TL_FIELD_W], c->d_alphas, c->d_betas, ra, rows, \
-                                                             rev ? 1 : 0, mask, *mc);                            \
+        TL_CUDA(tl_launch(k_cg_calc_pw<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],   \
+                          c->p2, c->f[TL_FIELD_R], c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W],        \
+                          c->d_alphas, c->d_betas, ra, rows, rev ? 1 : 0, mask, *mc));                          \
     else                                                                                                      \
-        k_cg_calc_pw<U, false><<<grid, TL_TPB, 0, c->stream>>>(c->g, c->f[TL_FIELD_P], c->p2, c->f[TL_FIELD_R],   \
-                                                              c->f[TL_FIELD_KX], c->f[TL_FIELD_KY],              \
-                                                              c->f[TL_FIELD_W], c->d_alphas, c->d_betas, ra,     \
-                                                              rows, rev ? 1 : 0, mask, g_single_ctx)
+        TL_CUDA(tl_launch(k_cg_calc_pw<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],  \
+                          c->p2, c->f[TL_FIELD_R], c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W],        \
+                          c->d_alphas, c->d_betas, ra, rows, rev ? 1 : 0, mask, g_single_ctx))
     switch (g_batch[TUNE_PW]) {
     case 1: LAUNCH_PW(1); break;
     case 2: LAUNCH_PW(2); break;
@@ -1545,9 +1311,9 @@ static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta
 {
     const int field = (mode == MODE_CHEBY) ? TL_FIELD_U : TL_FIELD_SD;
     TL_TRY(alt_buffer(c, field));
-    const int rows = tile_rows(c, TUNE_W);
-    dim3 grid = hot_grid(c, rows);
-    const int mask = external_mask(c);
+    const int rows = tlk_tile_rows(c, TUNE_W);
+    dim3 grid = tlk_hot_grid(c, rows);
+    const int mask = tlk_external_mask(c);
     if (mode == MODE_CHEBY)
         k_fused_stencil<MODE_CHEBY, 2><<<grid, TL_TPB, 0, c->stream>>>(
             c->g, c->f[TL_FIELD_U], c->alt[TL_FIELD_U], c->f[TL_FIELD_P], c->f[TL_FIELD_U0], c->f[TL_FIELD_R],

@@ -119,9 +119,21 @@ __global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test)
 }
 
 
+// Programmatic dependent launch of the resident loops' kernels (tl_device.cuh); TL_PDL=0 disables it (experiments).
+static bool use_pdl()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("TL_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_test, int batch, long* launches,
                                bool fused = false)
 {
+    const bool pdl = use_pdl();
     k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
     ++g_tl_launches;
     if (batch <= 0) batch = 32;
@@ -141,19 +153,19 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
         for (int it = 0; it < todo; ++it) {
             if (!fused) {
                 // cg_main_step_driver (cg_driver.c:69-124) + the p part of halo_update_driver (:22)
-                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false));
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true));
-                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true));
+                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, nullptr, pdl));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, nullptr, false, pdl));
+                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, nullptr, pdl));
                 *launches += 3;
             } else {
                 // iteration t >= 1 applies p = beta_{t-1} p + r inside the matvec kernel
                 if (enq + it == 0) {
-                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false));
+                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, nullptr, pdl));
                 } else {
-                    TL_TRY(tlk_cg_calc_pw(c, false));
+                    TL_TRY(tlk_cg_calc_pw(c, false, nullptr, pdl));
                     ++n_pw;
                 }
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, nullptr, false, pdl));
                 *launches += 2;
             }
         }
@@ -192,6 +204,7 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
 static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
                                      long* launches, bool fused = false)
 {
+    const bool pdl = use_pdl();
     k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
     ++g_tl_launches;
     if (batch <= 0) batch = 32;
@@ -210,19 +223,19 @@ static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, d
             mc.tl = enq + it - start;
             mc.it_global = enq + it;
             if (!fused) {
-                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc));
-                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc));
+                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc, pdl));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, false, pdl));
+                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc, pdl));
                 *launches += 3;
             } else {
                 // two kernels per iteration: r's halo (not p's) travels, the ring of updated p is recomputed
                 if (mc.tl == 0) {
-                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc));
+                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc, pdl));
                 } else {
-                    TL_TRY(tlk_cg_calc_pw(c, false, &mc));
+                    TL_TRY(tlk_cg_calc_pw(c, false, &mc, pdl));
                     ++n_pw;
                 }
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, true));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, true, pdl));
                 *launches += 2;
             }
         }

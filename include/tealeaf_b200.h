@@ -259,6 +259,11 @@ int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_launch);
  * (0 cg_calc_w, 1 cg_calc_ur, 2 cg_calc_p, 3 fused p+w). Results do not depend on `batch`;
  * reductions depend on `rows` only through the (deterministic) summation order. */
 int tl_set_tuning(int kernel, int rows, int batch);
+/* The fused p-update + matvec kernel of the resident CG loop: mode 0 (default) = register-staged kernel, mode 1 =
+ * TMA bulk-copy (cp.async.bulk) shared-memory row pipeline with persistent CTAs (measured equal, see tl_bulk.cu).  stages in {3,4,6,8} = rows in
+ * flight per CTA; ctas_per_sm 0 = as many as the shared-memory footprint allows (at most 8).  Results are
+ * bit-identical in every setting. */
+int tl_set_pw_pipeline(int mode, int stages, int ctas_per_sm);
 long tl_kernel_launch_count(void); /* kernels launched by this library in this process */
 /* CUDA-event timer on the chunk's own stream (torch.cuda.Event only sees torch's stream). */
 int tl_timer_start(tl_chunk* c);
