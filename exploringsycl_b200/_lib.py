@@ -111,6 +111,8 @@ SIGNATURES = {
     "tl_time_kernel": ([_vp, _i, _i, _pd], _i),
     "tl_set_tuning": ([_i, _i, _i], _i),
     "tl_set_pw_pipeline": ([_i, _i, _i], _i),
+    "tl_stamps_enable": ([_vp, _i], _i),
+    "tl_stamps_read": ([_vp, C.POINTER(C.c_ulonglong), _i], _i),
     "tl_kernel_launch_count": ([], C.c_long),
     "tl_timer_start": ([_vp], _i),
     "tl_timer_stop": ([_vp, _pd], _i),

@@ -133,6 +133,7 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h); cudaFreeHost(c->err_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas);
+    if (c->stamps) cudaFree(c->stamps);
     free(c->cg_alphas); free(c->cg_betas); free(c->cheby_alphas); free(c->cheby_betas);
     for (int fc = 0; fc < 4; ++fc) { cudaFree(c->face_send[fc]); cudaFree(c->face_recv[fc]); }
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
@@ -189,6 +190,36 @@ extern "C" int tl_array_read(tl_chunk* c, int array, double* host)
     const int len[4] = {c->g.x, c->g.y, c->g.x + 1, c->g.y + 1};
     TL_CUDA(cudaMemcpyAsync(host, src[array], (size_t)len[array] * 8, cudaMemcpyDeviceToHost, c->stream));
     TL_CUDA(cudaStreamSynchronize(c->stream));
+    return TL_OK;
+}
+
+// Resident-loop time stamps (DevScal.stamps, tl_internal.h): %globaltimer at four points of every loop kernel.
+extern "C" int tl_stamps_enable(tl_chunk* c, int iterations)
+{
+    TL_CHECK_ARG(c && iterations >= 0, "bad arguments");
+    TL_CUDA(cudaSetDevice(c->device));
+    TL_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->stamps) cudaFree(c->stamps);
+    c->stamps = nullptr;
+    c->stamp_cap = 0;
+    if (iterations > 0) {
+        const size_t n = (size_t)iterations * TL_STAMP_KERNELS * TL_STAMP_POINTS;
+        TL_CUDA(cudaMalloc((void**)&c->stamps, n * sizeof(unsigned long long)));
+        TL_CUDA(cudaMemset(c->stamps, 0, n * sizeof(unsigned long long)));
+        c->stamp_cap = iterations;
+    }
+    TL_CUDA(cudaMemcpy((char*)c->scal + offsetof(DevScal, stamps), &c->stamps, sizeof(c->stamps), cudaMemcpyHostToDevice));
+    TL_CUDA(cudaMemcpy((char*)c->scal + offsetof(DevScal, stamp_cap), &c->stamp_cap, sizeof(int), cudaMemcpyHostToDevice));
+    return TL_OK;
+}
+extern "C" int tl_stamps_read(tl_chunk* c, unsigned long long* host, int iterations)
+{
+    TL_CHECK_ARG(c && host && iterations >= 0 && iterations <= c->stamp_cap, "bad arguments");
+    TL_CUDA(cudaSetDevice(c->device));
+    TL_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)iterations * TL_STAMP_KERNELS * TL_STAMP_POINTS;
+    TL_CUDA(cudaMemcpy(host, c->stamps, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    TL_CUDA(cudaMemset(c->stamps, 0, n * sizeof(unsigned long long)));
     return TL_OK;
 }
 

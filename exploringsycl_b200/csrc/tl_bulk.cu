@@ -18,9 +18,9 @@
 //     updated p from the adjacent lanes by shuffle (the two edge lanes of a warp read them from the staged row instead
 //     of issuing scalar global loads), slide rows j-1, j, j+1 through registers and store w and p with 128-bit stores.
 //
-// Multi-rank (MULTI): the producer acquires the neighbours' halo flags before it stages the first row of an edge tile
-// (bulk copies read through L2, the point of coherence for NVLink peer stores, and never allocate in L1), the head
-// combines the ranks' r.r partials into beta and the tail publishes p.w exactly as k_cg_calc_pw does.
+// Multi-rank (MULTI): head and tail are k_cg_calc_pw's -- the neighbours' halo of r is in place when the preceding
+// calc_ur completes (its tail CTA acquires the halo flags; bulk copies read through L2, the point of coherence for
+// NVLink peer stores, and never allocate in L1), and the tail CTA combines the ranks' p.w partials.
 //
 // STATUS (round 2, measured on B200, profiles/pw_pipeline_r02.txt): bit-identical to the register-staged kernel on
 // every mesh tried, and exactly as fast under ncu (126.2 us vs 126.1 us at 4000^2, 749 MB of DRAM traffic and 72 % DRAM
@@ -168,44 +168,9 @@ k_cg_calc_pw_bulk(Geo g, const double* p_in, double* __restrict__ p_out, const d
     pdl_wait();
     pdl_trigger();
 
-    double beta;
-    bool skip;
-    if constexpr (!MULTI) {
-        skip = Sc->conv != 0;
-        beta = Sc->beta;
-    } else {
-        // Multi-rank head (as k_cg_calc_pw): beta_{t-1} = rrn_{t-1} / rro_{t-1} from all ranks' r.r partials in rank
-        // order; every CTA takes the same convergence decision from the same sum.
-        __shared__ int s_skip;
-        __shared__ double s_beta;
-        if (threadIdx.x < 32) {
-            bool sk = mc_skip(mc, Sc);
-            if (!sk) {
-                const double rro_prev = *(volatile double*)&Sc->rro_par[(mc.it_global - 1) & 1];
-                const double rrn = mc_sum_warp(mc, 1, mc.tl - 1, Sc);
-                const bool conv = conv_test(Sc, rrn);                 // cg_driver.c:24
-                if (threadIdx.x == 0) s_beta = rrn / rro_prev;        // cg_driver.c:106
-                if (threadIdx.x == 0 && blockIdx.x == 0) {            // bookkeeping of iteration t-1
-                    Sc->rrn = rrn;
-                    Sc->beta = rrn / rro_prev;
-                    d_betas[mc.it_global - 1] = rrn / rro_prev;       // cg_driver.c:111
-                    Sc->error = rrn;
-                    Sc->rro = rrn;
-                    Sc->rro_par[mc.it_global & 1] = rrn;              // cg_driver.c:123
-                    Sc->iters = mc.it_global;
-                    if (conv) {
-                        Sc->conv = 1;
-                        Sc->conv_iter = mc.it_global;
-                    }
-                }
-                if (conv) sk = true;
-            }
-            if (threadIdx.x == 0) s_skip = sk ? 1 : 0;
-        }
-        __syncthreads();
-        skip = s_skip != 0;
-        beta = s_beta;
-    }
+    // same head on one rank and on several (see k_cg_calc_pw): everything was settled by the preceding calc_ur's tail
+    const bool skip = sld(&Sc->conv) != 0;
+    const double beta = sld(&Sc->beta);
     if (skip) {
         // converged: this launch is a no-op, but the rows staged before the wait must land before the CTA (and its
         // shared memory) goes away
@@ -230,26 +195,8 @@ k_cg_calc_pw_bulk(Geo g, const double* p_in, double* __restrict__ p_out, const d
         // ------------------------------- producer warp (one elected lane) -------------------------------
         if (!producer) return;
         int it = 0;
-        [[maybe_unused]] int have = 0; // MULTI: faces whose halo flag has been acquired
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const TileGeo q = tile_geo(g, t, ntiles, gx, rows, rev);
-            if constexpr (MULTI) {
-                // edge tiles read the neighbours' halo of r (stored by their calc_ur of this iteration)
-                const int bx = q.tile % gx, by = q.tile / gx;
-                int need = 0;
-                if (bx == 0 && mc.nb_r[TL_FACE_LEFT]) need |= 1;
-                if (bx == gx - 1 && mc.nb_r[TL_FACE_RIGHT]) need |= 2;
-                if (by == 0 && mc.nb_r[TL_FACE_BOTTOM]) need |= 4;
-                if (by == gy - 1 && mc.nb_r[TL_FACE_TOP]) need |= 8;
-                need &= ~have;
-                if (need) {
-                    const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
-                    for (int f = 0; f < 4; ++f)
-                        if (need & (1 << f)) spin_flag(mc.hflags_local + f, want, Sc, 11ull + f);
-                    have |= need;
-                    asm volatile("fence.proxy.async.global;" ::: "memory"); // acquire (generic proxy) -> bulk reads (async proxy)
-                }
-            }
             for (int qq = 0; qq < q.nrow; ++qq, ++it) stage_row(it, q, qq, it < pre ? what_post : 15);
         }
         return;
@@ -334,18 +281,16 @@ k_cg_calc_pw_bulk(Geo g, const double* p_in, double* __restrict__ p_out, const d
             kyB = kyc;
         }
         double tot[1];
-        if (grid_reduce<1, true>(acc, ra, q.tile, ntiles, tot)) {
-            if constexpr (MULTI) {
-                if (threadIdx.x < 32) mc_publish_warp(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
-            }
+        if (grid_reduce<1, true>(acc, ra, q.tile, ntiles, tot) && threadIdx.x < 32) {
+            const int itn = sld(&Sc->iters);
+            double pw = tot[0];
+            if constexpr (MULTI) pw = mc_allsum_warp(mc, 0, tot[0], Sc); // sum_over_ranks(pw), cg_driver.c:85
             if (threadIdx.x == 0) {
-                Sc->pw = tot[0];
-                if constexpr (!MULTI) {
-                    const double alpha = Sc->rro / tot[0];
-                    Sc->alpha = alpha;
-                    d_alphas[Sc->iters] = alpha;
-                    Sc->p_pending = 0; // the pending p update of the previous iteration has now been applied
-                }
+                Sc->pw = pw;
+                const double alpha = Sc->rro / pw;
+                Sc->alpha = alpha;
+                d_alphas[itn] = alpha;
+                Sc->p_pending = 0; // the pending p update of the previous iteration has now been applied
             }
         }
     }

@@ -376,8 +376,7 @@ static int block_offset(const void* ptr, unsigned long long* off)
 //   recv[face 0..3][parity 0..1][face_elems] | tail:
 //   tail+0..3   flags of the generic halo exchange (by receiving face)
 //   tail+4..7   p-halo flags of the resident CG loop (by receiving face)
-//   tail+8..39  reduction slots  [kind][parity][rank]
-//   tail+40..71 reduction flags  [kind][parity][rank]
+//   tail+8..71  reduction cells  [kind][parity][rank] x 2 words {value half | sequence << 32} (MultiCtx, tl_internal.h)
 //   tail+72..75 ack flags of the generic halo exchange (by SENDING face: "message n of this face was unpacked")
 static size_t arena_recv_off(const tl_comms* k, int face, int parity)
 {
@@ -387,7 +386,6 @@ static size_t arena_flags_off(const tl_comms* k) { return (size_t)8 * k->face_el
 static size_t arena_total(const tl_comms* k) { return arena_flags_off(k) + 256; }
 #define ARENA_HFLAGS 4
 #define ARENA_SLOTS 8
-#define ARENA_SFLAGS 40
 #define ARENA_ACKS 72
 
 extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
@@ -453,13 +451,11 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
     mc.num_ranks = k->num_ranks;
     mc.rank = k->rank;
     double* tail = k->arena + arena_flags_off(k);
-    mc.slots_local = tail + ARENA_SLOTS;
-    mc.sflags_local = (unsigned long long*)(tail + ARENA_SFLAGS);
+    mc.slots_local = (unsigned long long*)(tail + ARENA_SLOTS);
     mc.hflags_local = (unsigned long long*)(tail + ARENA_HFLAGS);
     for (int r = 0; r < k->num_ranks; ++r) {
         double* ptail = (double*)k->peer_arena[r] + arena_flags_off(k);
-        mc.slots_peer[r] = ptail + ARENA_SLOTS;
-        mc.sflags_peer[r] = (unsigned long long*)(ptail + ARENA_SFLAGS);
+        mc.slots_peer[r] = (unsigned long long*)(ptail + ARENA_SLOTS);
     }
     for (int f = 0; f < 4; ++f) {
         const int n = c->nb[f];

@@ -90,8 +90,7 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
                 S->dbg[1] = want;
                 S->dbg[2] = seen;
                 S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
-                S->conv = 1;
-                S->conv_iter = 0; // mc_skip() is now true for every iteration: nothing computes on unknown data
+                S->conv = 1; // every later launch of the resident loop returns at once: nothing computes on unknown data
                 if (S->err_host) *(volatile unsigned int*)S->err_host = 0xdeadu;
                 __threadfence_system();
             }
@@ -118,6 +117,9 @@ __device__ __forceinline__ double ldp1(const double* p)
     if constexpr (COH) return __ldcg(p);
     else return __ldg(p);
 }
+// Solver scalars written by the tail CTA of the preceding kernel: read through L2 (see ldp2 above)
+__device__ __forceinline__ int sld(const int* p) { return __ldcg(p); }
+__device__ __forceinline__ double sld(const double* p) { return __ldcg(p); }
 struct RedArgs {
     double* partials;   // [NR][cap]   one per tile
     double* gpartials;  // [NR][gcap]  one per group of TL_RED_GROUP tiles
@@ -217,47 +219,100 @@ __device__ __forceinline__ double smvp(double kx0, double kx1, double ky0, doubl
 
 
 // ---------------------------------------------------------------------------------------------
-// Multi-rank helpers of the resident CG loop (see MultiCtx in tl_internal.h)
+// Multi-rank helpers of the resident loops (see MultiCtx in tl_internal.h)
 // ---------------------------------------------------------------------------------------------
-// Sum of the N ranks' partials of (kind, local iteration tl) in rank order.  Called by ALL 32 lanes of
-// warp 0: lane r waits for rank r's flag and loads its partial (the N memory latencies overlap), then
-// the partials are added in rank order, identically on every rank (same order as tl_comms_sum).
-__device__ __forceinline__ double mc_sum_warp(const MultiCtx& mc, int kind, int tl, DevScal* S)
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Optional time stamps of the resident loop (tl_stamps_enable): one thread, a few stores per kernel.
+__device__ __forceinline__ void stamp(DevScal* S, int iter, int kernel, int point)
+{
+    unsigned long long* st = S->stamps;
+    if (st && iter >= 0 && iter < S->stamp_cap)
+        st[((size_t)iter * TL_STAMP_KERNELS + kernel) * TL_STAMP_POINTS + point] = global_timer_ns();
+}
+
+// "LL" cell: a double travels as two 8-byte words {low half | seq << 32, high half | seq << 32} written by ONE 16-byte
+// store.  8-byte words are single-copy atomic, so a reader that finds the expected sequence number in BOTH words holds a
+// complete value: no fence, no separate flag, one NVLink hop.
+__device__ __forceinline__ void ll_store(unsigned long long* cell, double v, unsigned int seq)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = ((unsigned long long)seq << 32) | (b & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)seq << 32) | (b >> 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ bool ll_try_load(const unsigned long long* cell, unsigned int seq, double* v,
+                                            unsigned long long* seen)
+{
+    unsigned long long w0, w1;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(cell) : "memory");
+    *seen = w0;
+    if ((unsigned int)(w0 >> 32) != seq || (unsigned int)(w1 >> 32) != seq) return false;
+    *v = __longlong_as_double((long long)((w1 << 32) | (w0 & 0xffffffffull)));
+    return true;
+}
+// Spin until the cell carries `seq`; bounded like spin_flag (a lost peer is fatal for the solve, not for the GPU).
+__device__ __forceinline__ double ll_wait(const unsigned long long* cell, unsigned int seq, DevScal* S,
+                                          unsigned long long site)
+{
+    const long long t0 = clock64();
+    double v = 0.0;
+    unsigned long long seen = 0ull;
+    while (!ll_try_load(cell, seq, &v, &seen)) {
+        if (*(volatile unsigned int*)&S->pad == 0xdeadu) break;
+        if (clock64() - t0 > 20000000000LL) { // ~10 s
+            if (atomicCAS(&S->pad, 0u, 0xdeadu) == 0u) {
+                S->dbg[0] = site;
+                S->dbg[1] = seq;
+                S->dbg[2] = seen;
+                S->dbg[3] = (unsigned long long)(blockIdx.y * gridDim.x + blockIdx.x);
+                S->conv = 1;
+                if (S->err_host) *(volatile unsigned int*)S->err_host = 0xdeadu;
+                __threadfence_system();
+            }
+            break;
+        }
+        __nanosleep(32);
+    }
+    return v;
+}
+// sum_over_ranks (comms.c:55-61; cg_driver.c:85,104) inside the tail CTA of a reduction kernel.  Called by ALL 32 lanes
+// of warp 0: lane r stores this rank's partial into rank r's cell (its own included), then waits for rank r's partial
+// in the local copy (the N latencies overlap); the partials are added in rank order, identically on every rank.
+__device__ __forceinline__ double mc_allsum_warp(const MultiCtx& mc, int kind, double partial, DevScal* S)
 {
     const int lane = threadIdx.x & 31;
+    const unsigned long long n = mc.sbase + (unsigned long long)mc.tl + 1ull;
+    const unsigned int seq = (unsigned int)n;
+    const int par = (int)(n & 1ull);
     double v = 0.0;
     if (lane < mc.num_ranks) {
-        const int idx = TL_SLOT_IDX(kind, tl & 1, lane);
-        spin_flag(mc.sflags_local + idx, mc.sbase + (unsigned long long)tl + 1ull, S,
-                  1000ull + 100ull * kind + 10ull * lane + (unsigned long long)tl * 100000ull);
-        v = ld_volatile_f64(mc.slots_local + idx);
+        ll_store(mc.slots_peer[lane] + 2 * TL_SLOT_IDX(kind, par, mc.rank), partial, seq);
+        v = ll_wait(mc.slots_local + 2 * TL_SLOT_IDX(kind, par, lane), seq, S,
+                    1000ull + 100ull * kind + 10ull * lane + (unsigned long long)mc.tl * 100000ull);
     }
     double s = __shfl_sync(0xffffffffu, v, 0);
     for (int r = 1; r < mc.num_ranks; ++r) s = s + __shfl_sync(0xffffffffu, v, r);
     return s;
 }
-// Tail of a reduction kernel, called by all lanes of warp 0 of the last CTA: lane r stores this rank's
-// partial into rank r's slot, fences, then releases rank r's flag.
-__device__ __forceinline__ void mc_publish_warp(const MultiCtx& mc, int kind, double partial)
+// Tail CTA, after every CTA of the grid has fenced its remote halo stores and taken its ticket: threads 0..3 of the
+// calling warp release the neighbours' per-face flags (nbf[f] != null: that face has a neighbour) and then acquire
+// their own face's flag -- the neighbour's stores into MY halo are then visible to the next kernel.
+__device__ __forceinline__ void mc_halo_handshake(const MultiCtx& mc, double* const* nbf, DevScal* S, int lane)
 {
-    const int lane = threadIdx.x & 31;
-    if (lane < mc.num_ranks) {
-        const int idx = TL_SLOT_IDX(kind, mc.tl & 1, mc.rank);
-        mc.slots_peer[lane][idx] = partial;
-        __threadfence_system();
-        st_release_sys(mc.sflags_peer[lane] + idx, mc.sbase + (unsigned long long)mc.tl + 1ull);
+    if (lane < 4 && nbf[lane]) {
+        const unsigned long long n = mc.hbase + (unsigned long long)mc.tl + 1ull;
+        st_release_sys(mc.nb_hflag[lane], n);
+        spin_flag(mc.hflags_local + lane, n, S, 20ull + (unsigned long long)lane + (unsigned long long)mc.tl * 100000ull);
     }
 }
 __device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
 {
     return S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
-}
-// Head of every multi-rank kernel: is this launch a no-op?  Once calc_p of iteration X has seen
-// convergence it stamps conv_iter = X + 1; every later launch returns at once.  (One HBM-resident
-// scalar written in an earlier kernel: no peer traffic, no slot reads on this path.)
-__device__ __forceinline__ bool mc_skip(const MultiCtx& mc, const DevScal* S)
-{
-    return mc.it_global >= *(volatile const int*)&S->conv_iter;
 }
 
 // Hot-kernel tile: TL_TPB threads x 2 columns, `rows` rows.  kk is the first of the thread's two

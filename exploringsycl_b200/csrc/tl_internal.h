@@ -28,42 +28,53 @@ struct Geo {
 // kernels, read by the head of the next kernel: alpha/beta never visit the host inside a solve.
 struct DevScal {
     double rro, pw, rrn, alpha, beta, error, bb, eps;
-    double rro_par[2]; // multi-rank loop: rro of iteration t lives in rro_par[t & 1] (written one kernel earlier)
     double sums[8];
     int iters;         // CG iterations completed in this solve
-    int conv;          // set when sqrt(|rrn|) < eps (cg_driver.c:24)
+    int conv;          // set when sqrt(|rrn|) < eps (cg_driver.c:24) or iters reached max_iters: later launches are no-ops
     int p_pending;     // calc_ur ran: the matching calc_p must still run
     int max_iters;
-    int conv_iter;     // multi-rank loop: iterations >= conv_iter are no-ops (INT_MAX while running)
     int conv_mode;     // 0: sqrt(|rrn|) < eps (cg_driver.c:24); 1: |rrn| < eps (cheby_driver.c:70)
+    int norm_every;    // resident Chebyshev loop: sample the 2-norm when (iteration + 1) % norm_every == 0
     unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
     unsigned int pad;        // 0xdead: a peer wait timed out
     unsigned long long dbg[4]; // first timed-out wait: site, wanted value, seen value, block id
     unsigned int* err_host;  // mapped pinned host word: 0xdead is stored there as well, so the host sees a
                              // timed-out wait at its next synchronisation point without fetching DevScal
+    unsigned long long* stamps; // optional %globaltimer stamps of the resident loop kernels (tl_stamps_enable), else null
+    int stamp_cap;              // iterations the stamp buffer holds
 };
+// stamps[(iteration * TL_STAMP_KERNELS + kernel) * TL_STAMP_POINTS + point]
+//   kernel: 0 matvec (calc_w / calc_pw), 1 calc_ur, 2 calc_p
+//   point : 0 first CTA past its dependency wait, 1 tail CTA holds this rank's partial (all tiles done),
+//           2 all ranks' partials gathered (== 1 on one rank), 3 neighbours' halo flags seen / tail done
+#define TL_STAMP_KERNELS 3
+#define TL_STAMP_POINTS 4
 
 // Multi-rank context of the resident CG loop (passed by value to the hot kernels; num_ranks == 1
 // selects the single-GPU behaviour).  All peer pointers are CUDA-IPC mappings of the other ranks'
 // HBM: stores to them travel over NVLink / NVSwitch.
-//   slots : [kind 0 = p.w, 1 = r.r][parity][source rank] partial sums, one copy on EVERY rank.  The
-//           tail CTA of a reduction kernel stores its rank's partial into all ranks' copies and then
-//           releases a sequence flag; the head of the consumer kernel acquires the N flags and adds
-//           the N partials in rank order (bit-identical on every rank, same order as tl_comms_sum).
-//   halo  : calc_p stores its edge cells straight into the neighbour's halo cells of p; the last CTA
-//           to finish releases a per-face flag that the neighbour's edge tiles of calc_w acquire.
+//
+// All cross-rank waiting happens in the TAIL CTA of the producing kernel (the CTA that completes the
+// deterministic grid reduction); the heads of the kernels are exactly the single-GPU heads:
+//   slots : [kind 0 = p.w, 1 = r.r][parity][source rank] 16-byte cells, one copy on EVERY rank.  The tail
+//           CTA stores its rank's partial into all ranks' copies as two 8-byte words {value half, sequence}
+//           (the "LL" scheme of latency-optimised all-reduces: data and flag travel in ONE store, no fence, one
+//           NVLink hop), then spins on its own copy until all N cells carry this iteration's sequence number and
+//           adds the N partials in rank order (bit-identical on every rank, same order as tl_comms_sum).  It then
+//           writes alpha / beta / the convergence flag exactly as the single-GPU tail does.
+//   halo  : calc_p (three-kernel loop: p) or calc_ur (fused loop: r) stores its edge cells straight into the
+//           neighbour's halo cells; every CTA that made such stores fences them before its ticket, and the
+//           tail CTA releases the neighbours' per-face flags and then acquires its own: when the kernel
+//           completes, the halo this rank will read next is in place.
 #define TL_SLOT_IDX(kind, par, r) (((kind) * 2 + (par)) * TL_MAX_PEERS + (r))
 struct MultiCtx {
     int num_ranks, rank;
     int tl;                       // iteration index local to this resident call
-    int it_global;                // iteration index within the solve (cg_alphas / cg_betas index)
-    unsigned long long sbase;     // slot flag value of local iteration tl is sbase + tl + 1
-    unsigned long long hbase;     // halo flag value written after calc_p of local iteration tl is hbase + tl + 1
-    double* slots_local;
-    unsigned long long* sflags_local;
+    unsigned long long sbase;     // slot sequence number of local iteration tl is sbase + tl + 1
+    unsigned long long hbase;     // halo flag value released after local iteration tl is hbase + tl + 1
+    unsigned long long* slots_local;  // [TL_SLOT_IDX][2] words
     unsigned long long* hflags_local; // [4] by my face
-    double* slots_peer[TL_MAX_PEERS];
-    unsigned long long* sflags_peer[TL_MAX_PEERS];
+    unsigned long long* slots_peer[TL_MAX_PEERS];
     double* nb_p[4];              // neighbour's p field base (peer-mapped), by my face; null if external
     double* nb_r[4];              // neighbour's r field base (fused loop: r's halo is what travels)
     unsigned long long* nb_hflag[4]; // neighbour's halo flag of the opposite face
@@ -110,6 +121,8 @@ struct tl_chunk {
     unsigned int* err_h;             // pinned + mapped host word behind DevScal.err_host
     bool has_peers;
     int resident_iters;           // CG iterations enqueued so far in the current solve (host bookkeeping)
+    unsigned long long* stamps;   // device: optional %globaltimer stamps of the resident loop (tl_stamps_enable)
+    int stamp_cap;
 };
 
 // error handling ------------------------------------------------------------------------------

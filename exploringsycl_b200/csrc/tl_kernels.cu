@@ -464,7 +464,6 @@ __global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
     S->eps = eps;
     S->iters = 0;
     S->conv = 0;
-    S->conv_iter = 0x7fffffff;
     S->p_pending = 0;
     S->max_iters = max_iters;
     S->conv_mode = 0;
@@ -558,34 +557,15 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
             const MultiCtx mc)
 {
     DevScal* S = ra.S;
-    constexpr bool multi = MULTI;
     pdl_wait(); // p (and the solver scalars) come from the preceding kernels
     pdl_trigger();
-    if (mode == SCAL_DEV && !multi) {
-        const int conv = S->conv;
-        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) S->p_pending = 0;
-        if (conv) return;
-    }
-    if constexpr (MULTI) {
-        // converged already?  edge tiles: has the neighbour's calc_p delivered this iteration's halo of p?
-        __shared__ int s_skip;
-        if (threadIdx.x == 0) {
-            s_skip = mc_skip(mc, S) ? 1 : 0;
-            // The halo of p consumed by iteration it_global > 0 was stored by the neighbours' calc_p of iteration
-            // it_global - 1.  That holds for the first launch of a re-entered resident call too (cg_presteps steps one
-            // iteration at a time with no exchange in between): the previous call's last calc_p released hbase.
-            if (!s_skip && (mc.tl > 0 || mc.it_global > 0)) {
-                const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-                const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-                const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
-                if (bx == 0 && mc.nb_p[TL_FACE_LEFT]) spin_flag(mc.hflags_local + TL_FACE_LEFT, want, S, 1ull + (unsigned long long)mc.tl * 100000ull);
-                if (bx == gridDim.x - 1 && mc.nb_p[TL_FACE_RIGHT]) spin_flag(mc.hflags_local + TL_FACE_RIGHT, want, S, 2ull + (unsigned long long)mc.tl * 100000ull);
-                if (by == 0 && mc.nb_p[TL_FACE_BOTTOM]) spin_flag(mc.hflags_local + TL_FACE_BOTTOM, want, S, 3ull + (unsigned long long)mc.tl * 100000ull);
-                if (by == gridDim.y - 1 && mc.nb_p[TL_FACE_TOP]) spin_flag(mc.hflags_local + TL_FACE_TOP, want, S, 4ull + (unsigned long long)mc.tl * 100000ull);
-            }
+    if (mode == SCAL_DEV) {
+        const int conv = sld(&S->conv);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+            S->p_pending = 0;
+            if (!conv) stamp(S, sld(&S->iters), 0, 0);
         }
-        __syncthreads();
-        if (s_skip) return;
+        if (conv) return;
     }
     const HotTile t = hot_tile(g, rows, rev);
     double acc[1] = {0.0};
@@ -626,16 +606,18 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
         }
     }
     double tot[1];
-    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
-        if (multi) {
-            if (threadIdx.x < 32) mc_publish_warp(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
-        }
+    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot) && threadIdx.x < 32) {
+        const int it = (mode == SCAL_DEV) ? sld(&S->iters) : -1;
+        if (threadIdx.x == 0) stamp(S, it, 0, 1);
+        double pw = tot[0];
+        if constexpr (MULTI) pw = mc_allsum_warp(mc, 0, tot[0], S); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
         if (threadIdx.x == 0) {
-            S->pw = tot[0];
-            if (!multi && mode == SCAL_DEV) {
-                const double alpha = S->rro / tot[0]; // cg_driver.c:87
+            S->pw = pw;
+            if (mode == SCAL_DEV) {
+                const double alpha = S->rro / pw; // cg_driver.c:87
                 S->alpha = alpha;
-                d_alphas[S->iters] = alpha;           // cg_driver.c:93
+                d_alphas[it] = alpha;             // cg_driver.c:93
+                stamp(S, it, 0, 2);
             }
         }
     }
@@ -677,7 +659,6 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
              int rows, int rev, double* __restrict__ d_alphas, const MultiCtx mc, int send_r_halo)
 {
     DevScal* S = ra.S;
-    constexpr bool multi = MULTI;
     double alpha = alpha_imm;
     const HotTile t = hot_tile(g, rows, rev);
     const long pitch = g.pitch;
@@ -711,36 +692,12 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
     if (t.v0) load_ur(t.j0);
     pdl_wait();
     pdl_trigger();
-    if (mode == SCAL_DEV && !multi) {
-        if (S->conv) return;
-        alpha = S->alpha;
+    if (mode == SCAL_DEV) {
+        if (sld(&S->conv)) return;
+        alpha = sld(&S->alpha);
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) stamp(S, sld(&S->iters), 1, 0);
     }
     if (t.v0) load_pw(t.j0);
-    // The first batch of loads does not depend on alpha: it is issued BEFORE the multi-rank head, so the
-    // wait for the peers' p.w partials overlaps with this tile's HBM latency.
-    if constexpr (MULTI) {
-        __shared__ int s_skip;
-        __shared__ double s_alpha;
-        if (threadIdx.x < 32) {
-            const bool skip = mc_skip(mc, S);
-            if (!skip) {
-                const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
-                const double pw = mc_sum_warp(mc, 0, mc.tl, S);   // all ranks' p.w, rank order
-                if (threadIdx.x == 0) {
-                    s_alpha = rro / pw;                           // cg_driver.c:87
-                    if (blockIdx.x == 0 && blockIdx.y == 0) {
-                        S->pw = pw;
-                        S->alpha = s_alpha;
-                        d_alphas[mc.it_global] = s_alpha;         // cg_driver.c:93
-                    }
-                }
-            }
-            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_skip) return;
-        alpha = s_alpha;
-    }
     if (t.v0) {
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             if (jb != t.j0) load_batch(jb);
@@ -770,27 +727,31 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
     }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
-        if (multi) {
-            if (threadIdx.x < 32) mc_publish_warp(mc, 1, tot[0]); // sum_over_ranks(rrn), cg_driver.c:104, over NVLink
-            if (send_r_halo && threadIdx.x >= 32 && threadIdx.x < 36) { // every CTA fenced its halo stores before its ticket
-                const int f = threadIdx.x - 32;
-                if (mc.nb_r[f]) st_release_sys(mc.nb_hflag[f], mc.hbase + (unsigned long long)mc.tl + 1ull);
+        const int it = (mode == SCAL_DEV) ? sld(&S->iters) : -1;
+        if (threadIdx.x == 0) stamp(S, it, 1, 1);
+        double rrn = tot[0];
+        if constexpr (MULTI) {
+            // warp 0: sum_over_ranks(rrn), cg_driver.c:104, over NVLink; warp 1: fused loop, r's halo handshake (every CTA
+            // fenced its halo stores before its ticket)
+            if (threadIdx.x < 32) rrn = mc_allsum_warp(mc, 1, tot[0], S);
+            else if (send_r_halo && threadIdx.x < 64) {
+                mc_halo_handshake(mc, mc.nb_r, S, threadIdx.x - 32);
+                __syncwarp();
+                if (threadIdx.x == 32) stamp(S, it, 1, 3);
             }
         }
         if (threadIdx.x != 0) return;
-        S->rrn = tot[0];
-        if (multi) {
-        } else if (mode == SCAL_DEV) {
-            const double rrn = tot[0];
+        S->rrn = rrn;
+        if (mode == SCAL_DEV) {
             const double beta = rrn / S->rro; // cg_driver.c:106
             S->beta = beta;
-            d_betas[S->iters] = beta;         // cg_driver.c:111
+            d_betas[it] = beta;               // cg_driver.c:111
             S->error = rrn;                   // cg_driver.c:122-123
             S->rro = rrn;
-            S->iters = S->iters + 1;
+            S->iters = it + 1;
             S->p_pending = 1;
-            const bool hit = S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
-            if (hit || S->iters >= S->max_iters) S->conv = 1; // cg_driver.c:18,24; cheby_driver.c:70
+            if (conv_test(S, rrn) || it + 1 >= S->max_iters) S->conv = 1; // cg_driver.c:18,24; cheby_driver.c:70
+            stamp(S, it, 1, 2);
         }
     }
 }
@@ -860,6 +821,7 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
     const HotTile t = hot_tile(g, rows, rev);
     const long pitch = g.pitch;
     long i = t.i;
+    int it = -1;
     double2 pv[U], rv[U];
     auto load_p = [&](int jb) { // p: last written by the previous calc_p / calc_pw, at least two launches back
 #pragma unroll
@@ -878,41 +840,14 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
     if (t.v0) load_p(t.j0); // programmatic dependent launch: requested while calc_ur may still be draining
     pdl_wait();
     pdl_trigger();
-    if (mode == SCAL_DEV && !multi) {
-        if (!S->p_pending) return;
-        beta = S->beta;
+    if (mode == SCAL_DEV) {
+        if (!sld(&S->p_pending)) return;
+        beta = sld(&S->beta);
+        it = sld(&S->iters) - 1; // calc_ur of this iteration has already counted it
+        if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) stamp(S, it, 2, 0);
     }
     if (!MULTI && !t.v0) return;
-    if (t.v0) load_r(t.j0); // before the multi-rank head: overlaps the wait for the peers' r.r partials
-    if constexpr (MULTI) {
-        __shared__ int s_skip;
-        __shared__ double s_beta;
-        if (threadIdx.x < 32) {
-            const bool skip = mc_skip(mc, S);
-            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
-            if (!skip) {
-                const double rro = *(volatile double*)&S->rro_par[mc.it_global & 1];
-                const double rrn = mc_sum_warp(mc, 1, mc.tl, S);  // all ranks' r.r, rank order
-                if (threadIdx.x == 0) s_beta = rrn / rro;         // cg_driver.c:106
-                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { // bookkeeping for the host poll
-                    S->rrn = rrn;
-                    S->beta = rrn / rro;
-                    d_betas[mc.it_global] = rrn / rro;            // cg_driver.c:111
-                    S->error = rrn;                               // cg_driver.c:122-123
-                    S->rro = rrn;
-                    S->rro_par[(mc.it_global + 1) & 1] = rrn;     // read by the next iteration's kernels
-                    S->iters = mc.it_global + 1;
-                    if (conv_test(S, rrn) || mc.it_global + 1 >= S->max_iters) {
-                        S->conv = 1;
-                        S->conv_iter = mc.it_global + 1; // this launch (it_global) still completes
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (s_skip) return;
-        beta = s_beta;
-    }
+    if (t.v0) load_r(t.j0);
     if (t.v0) {
         const bool edge_tile = (halo_mask || multi) && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
                                                         blockIdx.x == gridDim.x - 1);
@@ -937,8 +872,9 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
         }
     }
     if constexpr (MULTI) {
-        // The last CTA to finish releases the per-face halo flags of the neighbours: every CTA makes its
-        // remote stores visible system-wide before taking its ticket.
+        // Every CTA makes its remote halo stores visible system-wide before taking its ticket; the last CTA to finish
+        // releases the neighbours' per-face flags and acquires its own: when this kernel completes, the halo of p that
+        // the next matvec reads is in place (what halo_update_driver.c:22 provides in the reference).
         __shared__ int s_last;
         const bool edge_cta = (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
         if (edge_cta) __threadfence_system(); // only edge tiles made remote stores
@@ -948,10 +884,12 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
             s_last = (tk == gridDim.x * gridDim.y - 1);
         }
         __syncthreads();
-        if (s_last && threadIdx.x < 4) {
+        if (s_last && threadIdx.x < 32) {
             if (threadIdx.x == 0) S->counter[1] = 0u;
-            if (mc.nb_p[threadIdx.x])
-                st_release_sys(mc.nb_hflag[threadIdx.x], mc.hbase + (unsigned long long)mc.tl + 1ull);
+            __threadfence();
+            mc_halo_handshake(mc, mc.nb_p, S, threadIdx.x);
+            __syncwarp();
+            if (threadIdx.x == 0) stamp(S, it, 2, 3);
         }
     }
 }
@@ -1009,55 +947,13 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
              const MultiCtx mc)
 {
     DevScal* S = ra.S;
-    double beta;
     pdl_wait(); // r comes from the calc_ur just before this kernel; w may not be overwritten while it still reads it
     pdl_trigger();
-    if constexpr (!MULTI) {
-        if (S->conv) return;
-        beta = S->beta;
-    } else {
-        // Multi-rank head: beta_{t-1} = rrn_{t-1} / rro_{t-1} from all ranks' r.r partials (rank order);
-        // every CTA takes the same convergence decision from the same sum.  The tiles are tall (one wave),
-        // so this runs once per CTA at kernel start.  Edge tiles then wait for the neighbours' r halo.
-        __shared__ int s_skip;
-        __shared__ double s_beta;
-        if (threadIdx.x < 32) {
-            bool skip = mc_skip(mc, S);
-            if (!skip) {
-                const double rro_prev = *(volatile double*)&S->rro_par[(mc.it_global - 1) & 1];
-                const double rrn = mc_sum_warp(mc, 1, mc.tl - 1, S);
-                const bool conv = conv_test(S, rrn);                  // cg_driver.c:24
-                if (threadIdx.x == 0) s_beta = rrn / rro_prev;        // cg_driver.c:106
-                if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) { // bookkeeping of iteration t-1
-                    S->rrn = rrn;
-                    S->beta = rrn / rro_prev;
-                    d_betas[mc.it_global - 1] = rrn / rro_prev;       // cg_driver.c:111
-                    S->error = rrn;
-                    S->rro = rrn;
-                    S->rro_par[mc.it_global & 1] = rrn;               // cg_driver.c:123
-                    S->iters = mc.it_global;
-                    if (conv) {
-                        S->conv = 1;
-                        S->conv_iter = mc.it_global;
-                    }
-                }
-                if (conv) skip = true;
-                if (!skip && threadIdx.x == 0) {
-                    const int by = rev ? (gridDim.y - 1 - blockIdx.y) : blockIdx.y;
-                    const int bx = rev ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
-                    const unsigned long long want = mc.hbase + (unsigned long long)mc.tl;
-                    if (bx == 0 && mc.nb_r[TL_FACE_LEFT]) spin_flag(mc.hflags_local + TL_FACE_LEFT, want, S, 11ull);
-                    if (bx == gridDim.x - 1 && mc.nb_r[TL_FACE_RIGHT]) spin_flag(mc.hflags_local + TL_FACE_RIGHT, want, S, 12ull);
-                    if (by == 0 && mc.nb_r[TL_FACE_BOTTOM]) spin_flag(mc.hflags_local + TL_FACE_BOTTOM, want, S, 13ull);
-                    if (by == gridDim.y - 1 && mc.nb_r[TL_FACE_TOP]) spin_flag(mc.hflags_local + TL_FACE_TOP, want, S, 14ull);
-                }
-            }
-            if (threadIdx.x == 0) s_skip = skip ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_skip) return;
-        beta = s_beta;
-    }
+    // Same head on one rank and on several: beta, the convergence flag and (multi-rank) the neighbours' halo of r were
+    // all settled by the tail CTA of the preceding calc_ur.
+    if (sld(&S->conv)) return;
+    const double beta = sld(&S->beta);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) stamp(S, sld(&S->iters), 0, 0);
     const HotTile t = hot_tile(g, rows, rev);
     const long pitch = g.pitch;
     const int lane = threadIdx.x & 31;
@@ -1148,17 +1044,18 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
         }
     }
     double tot[1];
-    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
-        if constexpr (MULTI) {
-            if (threadIdx.x < 32) mc_publish_warp(mc, 0, tot[0]); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
-        }
-        if (threadIdx.x != 0) return;
-        S->pw = tot[0];
-        if constexpr (!MULTI) {
-            const double alpha = S->rro / tot[0];
+    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot) && threadIdx.x < 32) {
+        const int it = sld(&S->iters);
+        if (threadIdx.x == 0) stamp(S, it, 0, 1);
+        double pw = tot[0];
+        if constexpr (MULTI) pw = mc_allsum_warp(mc, 0, tot[0], S); // sum_over_ranks(pw), cg_driver.c:85, over NVLink
+        if (threadIdx.x == 0) {
+            S->pw = pw;
+            const double alpha = S->rro / pw; // cg_driver.c:87
             S->alpha = alpha;
-            d_alphas[S->iters] = alpha;
+            d_alphas[it] = alpha;             // cg_driver.c:93
             S->p_pending = 0; // the pending p update of the previous iteration has now been applied
+            stamp(S, it, 0, 2);
         }
     }
 }

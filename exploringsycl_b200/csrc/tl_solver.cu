@@ -22,7 +22,6 @@ int tlc_halo_exchange(tl_chunk* c, tl_comms* k, const int fields[6], int depth);
 unsigned long long tlc_resident_seq_advance(tl_comms* k, int launched);
 
 __global__ void k_set_rro(DevScal* S, double rro) { S->rro = rro; }
-__global__ void k_clear_conv_stamp(DevScal* S) { S->conv_iter = 0x7fffffff; }
 
 static void fields_reset(int* f) { memset(f, 0, sizeof(int) * TL_NUM_EXCHANGE_FIELDS); }
 
@@ -105,19 +104,23 @@ static int cg_main_step_host(tl_chunk* c, tl_comms* k, int tt, double* rro, doub
     return TL_OK;
 }
 
-// Resident CG iterations on one rank: runs until `stop_iters` iterations are done or the
-// convergence test fires.  abs_test == 0: sqrt(|rrn|) < eps (cg_driver.c:24); abs_test == 1:
-// |rrn| < eps (cheby_driver.c:70, ppcg_driver.c:56).  On return the DevScal mirror is current.
+// Resident CG iterations: runs until `stop_iters` iterations are done or the convergence test fires.
+// abs_test == 0: sqrt(|rrn|) < eps (cg_driver.c:24); abs_test == 1: |rrn| < eps (cheby_driver.c:70,
+// ppcg_driver.c:56).  On return the DevScal mirror is current.
+//
+// One rank (k == null): three (or, fused, two) stream-ordered launches per iteration, alpha and beta never leave HBM.
+// N ranks: the SAME kernels and heads; p.w and r.r are combined across ranks inside the tail CTA of the reduction
+// kernels (every rank's partial is stored into every rank's slot array over NVLink, rank-ordered sum), and calc_p
+// (three kernels: p) or calc_ur (fused: r) stores its edge cells into the neighbours' halo and hand-shakes per face in
+// its tail.  No host round trip and no separate halo / all-reduce launches inside the loop; the host only polls the
+// convergence flag once per batch.
 __global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test)
 {
     S->max_iters = stop_iters;
     S->eps = eps;
     S->conv_mode = abs_test;
     S->conv = (S->iters >= stop_iters) ? 1 : 0;
-    S->conv_iter = S->conv ? S->iters : 0x7fffffff;
-    S->rro_par[S->iters & 1] = S->rro;
 }
-
 
 // Programmatic dependent launch of the resident loops' kernels (tl_device.cuh); TL_PDL=0 disables it (experiments).
 static bool use_pdl()
@@ -130,10 +133,11 @@ static bool use_pdl()
     return v == 1;
 }
 
-static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_test, int batch, long* launches,
-                               bool fused = false)
+static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
+                               long* launches, bool fused = false)
 {
     const bool pdl = use_pdl();
+    const bool multi = k && tl_comms_size(k) > 1 && c->has_peers;
     k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
     ++g_tl_launches;
     if (batch <= 0) batch = 32;
@@ -141,31 +145,40 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
     // so the GPU queue never drains; kernels launched after convergence return immediately.
     DevScal* snaps[2] = {c->scal_h + 1, c->scal_h + 2};
     cudaEvent_t ev[2] = {c->ev0, c->ev1};
-    int enq = c->resident_iters; // iterations already done in this solve
-    if (fused && enq != 0) {
+    const int start = c->resident_iters; // iterations already done in this solve
+    if (fused && start != 0) {
         tl_set_error("fused CG iterations must start at iteration 0 of a solve");
         return TL_ERR_ARG;
+    }
+    int enq = start;
+    MultiCtx mc = c->mc;
+    const MultiCtx* mcp = nullptr;
+    if (multi) {
+        mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
+        mcp = &mc;
     }
     int nb = 0, n_pw = 0;
     bool done = (enq >= stop_iters);
     while (!done) {
         const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
         for (int it = 0; it < todo; ++it) {
+            mc.tl = enq + it - start;
             if (!fused) {
                 // cg_main_step_driver (cg_driver.c:69-124) + the p part of halo_update_driver (:22)
-                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, nullptr, pdl));
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, nullptr, false, pdl));
-                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, nullptr, pdl));
+                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, mcp, pdl));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, mcp, false, pdl));
+                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, mcp, pdl));
                 *launches += 3;
             } else {
-                // iteration t >= 1 applies p = beta_{t-1} p + r inside the matvec kernel
+                // iteration t >= 1 applies p = beta_{t-1} p + r inside the matvec kernel; across ranks r's halo (not
+                // p's) travels and the ring of updated p is recomputed locally
                 if (enq + it == 0) {
-                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, nullptr, pdl));
+                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, mcp, pdl));
                 } else {
-                    TL_TRY(tlk_cg_calc_pw(c, false, nullptr, pdl));
+                    TL_TRY(tlk_cg_calc_pw(c, false, mcp, pdl));
                     ++n_pw;
                 }
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, nullptr, false, pdl));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, mcp, multi, pdl));
                 *launches += 2;
             }
         }
@@ -179,6 +192,9 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
         ++nb;
         if (enq >= stop_iters) done = true;
     }
+    // every rank launched the same iterations (the convergence decision comes from the same rank-ordered sums, and the
+    // poll of batch b happens after batch b + 1 was enqueued on every rank): the sequence bases stay in lockstep
+    if (multi) tlc_resident_seq_advance(k, enq - start);
     TL_TRY(tl_fetch_scal(c));
     c->resident_iters = c->scal_h->iters;
     if (fused) {
@@ -190,98 +206,13 @@ static int cg_iterate_resident(tl_chunk* c, int stop_iters, double eps, int abs_
             c->f[TL_FIELD_P] = c->p2;
             c->p2 = tmp;
         }
-        // the last iteration's p update is still pending (cg_driver.c:115) -- apply it, with its halo
+        // the last iteration's p update is still pending (cg_driver.c:115) -- apply it, with its reflective halo; the
+        // caller's halo update (cg_driver.c:22) refreshes the halos shared with neighbouring ranks
         TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true));
         *launches += 1;
-    }
-    return TL_OK;
-}
-
-// Resident CG iterations on N ranks: the same three kernels, but p.w and r.r are combined across
-// ranks inside the kernels (tail CTA -> every rank's slots over NVLink -> head of the next kernel) and
-// calc_p stores its edge cells into the neighbours' halo of p.  No host round trip and no separate
-// halo / all-reduce launches inside the loop; the host only polls the convergence flag per batch.
-static int cg_iterate_resident_multi(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
-                                     long* launches, bool fused = false)
-{
-    const bool pdl = use_pdl();
-    k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
-    ++g_tl_launches;
-    if (batch <= 0) batch = 32;
-    DevScal* snaps[2] = {c->scal_h + 1, c->scal_h + 2};
-    cudaEvent_t ev[2] = {c->ev0, c->ev1};
-    const int start = c->resident_iters;
-    if (fused && start != 0) fused = false; // the fused kernel needs the previous iteration's r.r slots
-    int enq = start;
-    MultiCtx mc = c->mc;
-    mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
-    int nb = 0, n_pw = 0;
-    bool done = (enq >= stop_iters);
-    while (!done) {
-        const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
-        for (int it = 0; it < todo; ++it) {
-            mc.tl = enq + it - start;
-            mc.it_global = enq + it;
-            if (!fused) {
-                TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc, pdl));
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, false, pdl));
-                TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &mc, pdl));
-                *launches += 3;
-            } else {
-                // two kernels per iteration: r's halo (not p's) travels, the ring of updated p is recomputed
-                if (mc.tl == 0) {
-                    TL_TRY(tlk_cg_calc_w(c, SCAL_DEV, false, &mc, pdl));
-                } else {
-                    TL_TRY(tlk_cg_calc_pw(c, false, &mc, pdl));
-                    ++n_pw;
-                }
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, &mc, true, pdl));
-                *launches += 2;
-            }
-        }
-        enq += todo;
-        TL_CUDA(cudaMemcpyAsync(snaps[nb & 1], c->scal, sizeof(DevScal), cudaMemcpyDeviceToHost, c->stream));
-        TL_CUDA(cudaEventRecord(ev[nb & 1], c->stream));
-        if (nb > 0) {
-            TL_CUDA(cudaEventSynchronize(ev[(nb - 1) & 1]));
-            if (snaps[(nb - 1) & 1]->conv) done = true;
-        }
-        ++nb;
-        if (enq >= stop_iters) done = true;
-    }
-    tlc_resident_seq_advance(k, enq - start); // identical on every rank: the poll sees the same flag
-    TL_TRY(tl_fetch_scal(c));
-    if (fused) {
-        // iterations actually executed: up to the convergence stamp, else everything that was launched
-        const int executed = c->scal_h->conv ? c->scal_h->conv_iter : enq;
-        const int executed_pw = executed > 0 ? executed - 1 : 0;
-        if ((n_pw - executed_pw) & 1) { // undo the host-side P/P2 swaps of launches that were no-ops
-            double* tmp = c->f[TL_FIELD_P];
-            c->f[TL_FIELD_P] = c->p2;
-            c->p2 = tmp;
-        }
-        if (executed > 0) {
-            // the last iteration's p update (and its bookkeeping: beta, error, iteration count) is pending
-            MultiCtx fin = mc;
-            fin.tl = executed - 1 - start;
-            fin.it_global = executed - 1;
-            for (int f = 0; f < 4; ++f) fin.nb_p[f] = nullptr; // halos are refreshed by the generic exchange below
-            k_clear_conv_stamp<<<1, 1, 0, c->stream>>>(c->scal);
-            ++g_tl_launches;
-            TL_TRY(tlk_cg_calc_p(c, SCAL_DEV, 0.0, false, true, &fin));
-            *launches += 1;
-            TL_TRY(tl_fetch_scal(c));
-        }
         // Neighbours address this chunk's p through the slab mapping (three-kernel loop): leave p there.
-        double* slab_p = c->slab + (size_t)TL_FIELD_P * c->field_elems;
-        if (c->f[TL_FIELD_P] != slab_p) {
-            TL_CUDA(cudaMemcpyAsync(slab_p, c->f[TL_FIELD_P], c->field_elems * sizeof(double),
-                                    cudaMemcpyDeviceToDevice, c->stream));
-            c->p2 = c->f[TL_FIELD_P];
-            c->f[TL_FIELD_P] = slab_p;
-        }
+        if (multi) TL_TRY(tlk_field_home(c, TL_FIELD_P));
     }
-    c->resident_iters = c->scal_h->iters;
     if (c->scal_h->pad == 0xdeadu) {
         tl_set_error("resident CG loop: timed out waiting for a peer rank (site %llu want %llu seen %llu block %llu, "
                      "iters %d)", c->scal_h->dbg[0], c->scal_h->dbg[1], c->scal_h->dbg[2], c->scal_h->dbg[3],
@@ -333,7 +264,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
     if (!multi) {
         // p's reflective halo is written by calc_p itself; u's halo is only read after the loop
         // (calculate_residual, solve_finished_driver.c:19), so it is refreshed once at the end.
-        TL_TRY(cg_iterate_resident(c, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w != 0));
+        TL_TRY(cg_iterate_resident(c, nullptr, o->max_iters, o->eps, 0, o->batch, &launches, o->fuse_p_into_w != 0));
         const DevScal* S = c->scal_h;
         error = S->error;
         const bool converged = sqrt(fabs(error)) < o->eps;
@@ -343,7 +274,7 @@ static int cg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double rx,
         TL_TRY(fetch_cg_coeffs(c, S->iters));
     } else if (use_resident_multi(c, k)) {
         const bool fuse_multi = tl_cg_loop_is_fused(c, o->fuse_p_into_w) != 0;
-        TL_TRY(cg_iterate_resident_multi(c, k, o->max_iters, o->eps, 0, o->batch, &launches, fuse_multi));
+        TL_TRY(cg_iterate_resident(c, k, o->max_iters, o->eps, 0, o->batch, &launches, fuse_multi));
         const DevScal* S = c->scal_h;
         error = S->error;
         const bool converged = sqrt(fabs(error)) < o->eps;
@@ -473,8 +404,7 @@ static int cg_presteps(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, int* fi
     *ended = false;
     const bool resident = !multi || use_resident_multi(c, k);
     auto iterate = [&](int stop, int bt) {
-        return multi ? cg_iterate_resident_multi(c, k, stop, o->eps, 1, bt, launches)
-                     : cg_iterate_resident(c, stop, o->eps, 1, bt, launches);
+        return cg_iterate_resident(c, multi ? k : nullptr, stop, o->eps, 1, bt, launches);
     };
     if (resident) {
         // The rule cannot fire before tt = presteps+1 (or 21 with error_switch): run that many

@@ -264,6 +264,12 @@ int tl_set_tuning(int kernel, int rows, int batch);
  * flight per CTA; ctas_per_sm 0 = as many as the shared-memory footprint allows (at most 8).  Results are
  * bit-identical in every setting. */
 int tl_set_pw_pipeline(int mode, int stages, int ctas_per_sm);
+/* Profiling aid: the kernels of the resident CG loop record %globaltimer (ns) at four points -- first CTA past its
+ * dependency wait, tail CTA holds this rank's partial sum, all ranks' partials gathered, halo hand-shake done -- for the
+ * first `iterations` iterations of every solve (0 disables).  tl_stamps_read copies out
+ * [iteration][kernel: 0 matvec, 1 calc_ur, 2 calc_p][point 0..3] and clears the buffer. */
+int tl_stamps_enable(tl_chunk* c, int iterations);
+int tl_stamps_read(tl_chunk* c, unsigned long long* host, int iterations);
 long tl_kernel_launch_count(void); /* kernels launched by this library in this process */
 /* CUDA-event timer on the chunk's own stream (torch.cuda.Event only sees torch's stream). */
 int tl_timer_start(tl_chunk* c);
