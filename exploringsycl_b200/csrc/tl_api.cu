@@ -75,10 +75,13 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
     c->field_elems = ((size_t)g.off + (size_t)g.y * g.pitch + 64 + 31) / 32 * 32; // 256-byte multiple
     // One slab for all fields, a 2 MiB multiple: it is its own allocation block, so one CUDA-IPC handle
     // maps every field of this chunk into the neighbouring ranks (tl_comms_attach_chunk).
-    c->slab_bytes = (c->field_elems * sizeof(double) * TL_NUM_FIELDS + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    c->slab_bytes = (c->field_elems * sizeof(double) * TL_SLAB_SLOTS + (2u << 20) - 1) / (2u << 20) * (2u << 20);
     TL_CUDA(cudaMalloc((void**)&c->slab, c->slab_bytes));
     TL_CUDA(cudaMemset(c->slab, 0, c->slab_bytes));
     for (int f = 0; f < TL_NUM_FIELDS; ++f) c->f[f] = c->slab + (size_t)f * c->field_elems;
+    c->p2 = c->slab + (size_t)TL_SLAB_P2 * c->field_elems;
+    c->alt[TL_FIELD_U] = c->slab + (size_t)TL_SLAB_U2 * c->field_elems;
+    c->alt[TL_FIELD_SD] = c->slab + (size_t)TL_SLAB_SD2 * c->field_elems;
     TL_TRY(dev_zalloc(&c->cell_x, g.x + 2));
     TL_TRY(dev_zalloc(&c->cell_y, g.y + 2));
     TL_TRY(dev_zalloc(&c->vertex_x, g.x + 2));
@@ -127,9 +130,6 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->slab);
-    if (c->p2_alloc) cudaFree(c->p2_alloc);
-    for (int f = 0; f < TL_NUM_FIELDS; ++f)
-        if (c->alt_alloc[f]) cudaFree(c->alt_alloc[f]);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h); cudaFreeHost(c->err_h);
     cudaFree(c->d_alphas); cudaFree(c->d_betas);

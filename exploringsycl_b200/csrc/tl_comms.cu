@@ -460,6 +460,7 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
     for (int f = 0; f < 4; ++f) {
         const int n = c->nb[f];
         c->nb_recv[f] = nullptr;
+        c->nb_slab[f] = nullptr;
         c->nb_flag[f] = nullptr;
         c->nb_ack[f] = nullptr;
         c->my_ack[f] = (unsigned long long*)(tail + ARENA_ACKS) + f;
@@ -468,8 +469,8 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
         c->nb_recv[f] = base + arena_recv_off(k, opposite[f], 0);
         c->nb_flag[f] = (unsigned long long*)(base + arena_flags_off(k)) + opposite[f];
         c->nb_ack[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_ACKS) + opposite[f];
-        mc.nb_p[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_P * h->field_elems[n];
-        mc.nb_r[f] = (double*)k->peer_pfield[n] + (size_t)TL_FIELD_R * h->field_elems[n];
+        c->nb_slab[f] = (double*)k->peer_pfield[n];
+        c->nb_field_elems[f] = h->field_elems[n];
         mc.nb_hflag[f] = (unsigned long long*)(base + arena_flags_off(k) + ARENA_HFLAGS) + opposite[f];
         mc.nb_x[f] = h->geo[n][0];
         mc.nb_y[f] = h->geo[n][1];

@@ -310,6 +310,34 @@ __device__ __forceinline__ void mc_halo_handshake(const MultiCtx& mc, double* co
         spin_flag(mc.hflags_local + lane, n, S, 20ull + (unsigned long long)lane + (unsigned long long)mc.tl * 100000ull);
     }
 }
+// "Last CTA of the grid" ticket for kernels without a reduction (calc_p, the one-pass Chebyshev / PPCG kernels), two
+// levels like grid_reduce so that thousands of CTAs do not queue on one address: tiles take a ticket of their group of
+// TL_RED_GROUP, the last tile of a group takes a ticket of the grid.  Every CTA calls it after its last store (remote
+// halo stores already fenced system-wide); returns true in every thread of the last CTA to arrive.
+__device__ __forceinline__ bool grid_last_cta(unsigned int* gcount, unsigned int* counter, int tile, int ntiles)
+{
+    __shared__ int s_last_cta;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int group = tile / TL_RED_GROUP;
+        const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
+        const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
+        int last = 0;
+        __threadfence();
+        if (atomicAdd(&gcount[group], 1u) == (unsigned int)(gsize - 1)) {
+            gcount[group] = 0u;
+            __threadfence();
+            if (atomicAdd(counter, 1u) == (unsigned int)(ngroups - 1)) {
+                *counter = 0u;
+                last = 1;
+            }
+        }
+        s_last_cta = last;
+    }
+    __syncthreads();
+    if (s_last_cta) __threadfence();
+    return s_last_cta != 0;
+}
 __device__ __forceinline__ bool conv_test(const DevScal* S, double rrn)
 {
     return S->conv_mode ? (fabs(rrn) < S->eps) : (sqrt(fabs(rrn)) < S->eps);
@@ -367,3 +395,11 @@ __device__ __forceinline__ void edge_remote_store(const Geo& g, const MultiCtx& 
     }
 }
 
+// Did this tile make remote halo stores, i.e. does it own cells on a face that has a neighbour?  (Those tiles fence
+// their stores system-wide before they take their end-of-kernel ticket.)
+__device__ __forceinline__ bool tile_sends_halo(const Geo& g, const MultiCtx& mc, const HotTile& t)
+{
+    return (t.kk - 2 * (int)threadIdx.x == g.hd && mc.nb_f[TL_FACE_LEFT]) ||
+           (t.kk - 2 * (int)threadIdx.x + TL_TILE_COLS >= g.x - g.hd && mc.nb_f[TL_FACE_RIGHT]) ||
+           (t.j0 == g.hd && mc.nb_f[TL_FACE_BOTTOM]) || (t.j1 == g.y - g.hd && mc.nb_f[TL_FACE_TOP]);
+}

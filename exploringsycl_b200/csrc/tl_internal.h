@@ -20,6 +20,13 @@ struct Geo {
     int pitch, off; // row pitch and lead offset, in doubles
 };
 
+// Slab slots: the TL_NUM_FIELDS public fields, then the second buffers of the double-buffered in-place updates.  They
+// live in the slab so that ONE CUDA-IPC mapping lets a neighbour store halo cells into whichever buffer is current.
+#define TL_SLAB_P2 (TL_NUM_FIELDS + 0)
+#define TL_SLAB_U2 (TL_NUM_FIELDS + 1)
+#define TL_SLAB_SD2 (TL_NUM_FIELDS + 2)
+#define TL_SLAB_SLOTS (TL_NUM_FIELDS + 3)
+
 #define TL_TPB 128          // threads per CTA of the streaming kernels
 #define TL_TILE_COLS 256    // 2 cells per thread
 #define TL_MAX_PEERS 8
@@ -75,8 +82,9 @@ struct MultiCtx {
     unsigned long long* slots_local;  // [TL_SLOT_IDX][2] words
     unsigned long long* hflags_local; // [4] by my face
     unsigned long long* slots_peer[TL_MAX_PEERS];
-    double* nb_p[4];              // neighbour's p field base (peer-mapped), by my face; null if external
-    double* nb_r[4];              // neighbour's r field base (fused loop: r's halo is what travels)
+    double* nb_f[4];              // neighbour's copy of the field whose halo travels in this launch (peer-mapped base),
+                                  // by my face; null if the face is external.  Set per launch: p (calc_p), r (fused
+                                  // calc_ur), the updated u / sd buffer (one-pass Chebyshev / PPCG kernels)
     unsigned long long* nb_hflag[4]; // neighbour's halo flag of the opposite face
     int nb_pitch[4], nb_x[4], nb_y[4], nb_off[4];
 };
@@ -93,10 +101,11 @@ struct tl_chunk {
     size_t slab_bytes;
     double* f[TL_NUM_FIELDS];     // device, slab + f * field_elems (P may point to p2 in fused mode)
     double *cell_x, *cell_y, *vertex_x, *vertex_y; // device 1-D
-    double* p2;                   // device, second p buffer of the fused p+w kernel (lazily allocated)
-    double* p2_alloc;             // the allocation behind it (P and P2 swap roles; this is what gets freed)
-    double* alt[TL_NUM_FIELDS];   // second buffers of the fused Chebyshev (U) / PPCG (SD) kernels, lazily allocated
-    double* alt_alloc[TL_NUM_FIELDS];
+    double* p2;                   // second p buffer of the fused p+w kernel (slab slot TL_SLAB_P2; P and P2 swap roles)
+    double* alt[TL_NUM_FIELDS];   // second buffers of the one-pass Chebyshev (U) / PPCG (SD) kernels (slab slots
+                                  // TL_SLAB_U2 / TL_SLAB_SD2; a field and its alternate swap roles every launch)
+    double* nb_slab[4];           // neighbours' slabs (peer-mapped), by my face; null if external or not attached
+    size_t nb_field_elems[4];     // doubles per field inside that neighbour's slab
     double* partials;             // device, per-tile partial sums (4 lanes)
     int partial_cap;              // tiles
     double* gpartials;            // device, per-group (64 tiles) sums (4 lanes)
@@ -167,12 +176,18 @@ int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry);  // -> scal
 int tlk_cg_calc_w(tl_chunk* c, ScalMode mode, bool rev, const MultiCtx* mc = nullptr, bool pdl = false);                // -> scal->pw (& alpha when SCAL_DEV)
 int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const MultiCtx* mc = nullptr, bool send_r_halo = false, bool pdl = false); // -> scal->rrn (& beta, conv when SCAL_DEV)
 int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc = nullptr, bool pdl = false);
+// neighbours' peer-mapped copy of the buffer `buf` of this chunk (a slab slot), by face, into mc->nb_f
+void tlk_set_travelling_field(const tl_chunk* c, MultiCtx* mc, const double* buf);
 int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc = nullptr, bool pdl = false);                             // fused p-update + matvec (SCAL_DEV only); swaps P/P2
 int tlk_cheby_init(tl_chunk* c, double theta);
 int tlk_cheby_iterate(tl_chunk* c, double alpha, double beta);
 int tlk_cheby_calc_u(tl_chunk* c);
-int tlk_cheby_fused(tl_chunk* c, double alpha, double beta);  // cheby_iterate + cheby_calc_u in one pass; swaps U buffers
-int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta);   // ppcg_calc_ur + ppcg_calc_sd in one pass; swaps SD buffers
+// cheby_iterate + cheby_calc_u in one pass (swaps the U buffers) / ppcg_calc_ur + ppcg_calc_sd in one pass (swaps the SD
+// buffers).  mc != null: the updated operand's edge cells are stored into the neighbours' halo and the kernel's last CTA
+// hand-shakes with them (no separate halo exchange).  norm: also sum r.r over the interior (all ranks when mc) ->
+// scal->sums[0].
+int tlk_cheby_fused(tl_chunk* c, double alpha, double beta, const MultiCtx* mc = nullptr, bool norm = false);
+int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta, const MultiCtx* mc = nullptr, bool norm = false);
 int tlk_field_home(tl_chunk* c, int field);                   // move a double-buffered field back into the slab
 int tlk_ppcg_init(tl_chunk* c, double theta);
 int tlk_ppcg_calc_ur(tl_chunk* c);

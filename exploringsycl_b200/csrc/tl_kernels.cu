@@ -64,6 +64,75 @@ static int launch_generic(tl_chunk* c, int k_lo, int k_hi, int j_lo, int j_hi, F
     return TL_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vectorised row-tiled kernel for the streaming / reduction kernels outside the CG loop: two columns per thread
+// (double2, 16-byte aligned: the first column of a thread is chosen so that off + kk is even), `rows` rows per CTA,
+// and the loads of U rows are issued back to back before any of them is consumed (LD returns a plain struct V of
+// loaded values, AP consumes it): the scalar one-row-at-a-time skeleton above keeps 8 bytes per thread in flight and
+// reaches 45-75 % of the HBM peak on these kernels, this one 16 x (fields) x U.
+// LD: V (long i, int jj, int kk).  AP: (const V&, long i, int jj, int kk, bool v0, bool v1, double* acc); v0 / v1 say
+// which of the thread's two columns lie inside [k_lo, k_hi).  Per-thread accumulation order is row-major, column 0
+// before column 1 (what the oracle's replay of the reduction tree assumes for the two-column tile).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_mask(double* p, double2 v, bool v0, bool v1)
+{
+    if (v0 && v1) st2(p, v);
+    else if (v0) p[0] = v.x;
+    else if (v1) p[1] = v.y;
+}
+template <int NR, int U, class V, class LD, class AP, class Fin>
+__global__ void __launch_bounds__(TL_TPB) k_vec(Geo g, int kbase, int k_lo, int k_hi, int j_lo, int j_hi, int rows,
+                                                LD ld, AP ap, Fin fin, RedArgs ra)
+{
+    const int kk = kbase + 2 * (blockIdx.x * TL_TPB + threadIdx.x);
+    const bool v0 = kk >= k_lo && kk < k_hi, v1 = kk + 1 >= k_lo && kk + 1 < k_hi;
+    const int j0 = j_lo + blockIdx.y * rows;
+    const int j1 = min(j0 + rows, j_hi);
+    double acc[NR > 0 ? NR : 1];
+#pragma unroll
+    for (int r = 0; r < (NR > 0 ? NR : 1); ++r) acc[r] = 0.0;
+    if (v0 || v1) {
+        long i = (long)g.off + (long)j0 * g.pitch + kk;
+        for (int jb = j0; jb < j1; jb += U, i += (long)U * g.pitch) {
+            V vals[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (jb + u < j1) vals[u] = ld(i + (long)u * g.pitch, jb + u, kk);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (jb + u < j1) ap(vals[u], i + (long)u * g.pitch, jb + u, kk, v0, v1, acc);
+        }
+    }
+    if constexpr (NR > 0) {
+        double tot[NR > 0 ? NR : 1];
+        const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        if (grid_reduce<(NR > 0 ? NR : 1)>(acc, ra, tile, gridDim.x * gridDim.y, tot) && threadIdx.x == 0)
+            fin(tot, ra.S);
+    }
+}
+
+template <int NR, int U, class V, class LD, class AP, class Fin>
+static int launch_vec(tl_chunk* c, int k_lo, int k_hi, int j_lo, int j_hi, LD ld, AP ap, Fin fin)
+{
+    if (k_hi <= k_lo || j_hi <= j_lo) return TL_OK;
+    const int rows = 8;
+    const int kbase = k_lo - ((c->g.off + k_lo) & 1);
+    dim3 grid((k_hi - kbase + TL_TILE_COLS - 1) / TL_TILE_COLS, (j_hi - j_lo + rows - 1) / rows);
+    if (NR > 0 && (long)grid.x * grid.y > c->partial_cap) {
+        tl_set_error("partials capacity exceeded");
+        return TL_ERR_ARG;
+    }
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
+    k_vec<NR, U, V, LD, AP, Fin><<<grid, TL_TPB, 0, c->stream>>>(c->g, kbase, k_lo, k_hi, j_lo, j_hi, rows, ld, ap, fin, ra);
+    ++g_tl_launches;
+    TL_CUDA(cudaGetLastError());
+    return TL_OK;
+}
+struct V1 { double2 a; };
+struct V2 { double2 a, b; };
+struct V3 { double2 a, b, c; };
+struct V4 { double2 a, b, c, d; };
+
 #define INTERIOR_RANGE(c) (c)->g.hd, (c)->g.x - (c)->g.hd, (c)->g.hd, (c)->g.y - (c)->g.hd
 #define ALL_RANGE(c) 0, (c)->g.x, 0, (c)->g.y
 
@@ -152,9 +221,10 @@ int tlk_copy_field(tl_chunk* c, int dst, int src, bool interior_only)
 {
     double* D = c->f[dst];
     const double* S = c->f[src];
-    auto f = [=] __device__(long i, int, int, double*) { D[i] = S[i]; };
-    if (interior_only) return launch_generic<0>(c, INTERIOR_RANGE(c), f, NoFin());
-    return launch_generic<0>(c, ALL_RANGE(c), f, NoFin());
+    auto ld = [=] __device__(long i, int, int) { return V1{ld2(S + i)}; };
+    auto ap = [=] __device__(const V1& v, long i, int, int, bool v0, bool v1, double*) { st_mask(D + i, v.a, v0, v1); };
+    if (interior_only) return launch_vec<0, 4, V1>(c, INTERIOR_RANGE(c), ld, ap, NoFin());
+    return launch_vec<0, 4, V1>(c, ALL_RANGE(c), ld, ap, NoFin());
 }
 
 // field_summary.cpp:6-151
@@ -162,15 +232,26 @@ int tlk_field_summary(tl_chunk* c)
 {
     const double *vol = c->f[TL_FIELD_VOLUME], *den = c->f[TL_FIELD_DENSITY], *e0 = c->f[TL_FIELD_ENERGY0],
                  *u = c->f[TL_FIELD_U];
-    return launch_generic<4>(
+    return launch_vec<4, 2, V4>(
         c, INTERIOR_RANGE(c),
-        [=] __device__(long i, int, int, double* acc) {
-            const double cv = vol[i];
-            const double cm = cv * den[i];
-            acc[0] += cv;
-            acc[1] += cm;
-            acc[2] += cm * e0[i];
-            acc[3] += cm * u[i];
+        [=] __device__(long i, int, int) { return V4{ld2(vol + i), ld2(den + i), ld2(e0 + i), ld2(u + i)}; },
+        [=] __device__(const V4& v, long, int, int, bool v0, bool v1, double* acc) {
+            if (v0) {
+                const double cv = v.a.x;
+                const double cm = cv * v.b.x;
+                acc[0] += cv;
+                acc[1] += cm;
+                acc[2] += cm * v.c.x;
+                acc[3] += cm * v.d.x;
+            }
+            if (v1) {
+                const double cv = v.a.y;
+                const double cm = cv * v.b.y;
+                acc[0] += cv;
+                acc[1] += cm;
+                acc[2] += cm * v.c.y;
+                acc[3] += cm * v.d.y;
+            }
         },
         [=] __device__(const double* t, DevScal* S) {
             S->sums[0] = t[0];
@@ -412,38 +493,53 @@ int tlk_phase_exchange(tl_chunk* c, const int fields[6], int depth, bool send, c
 // ---------------------------------------------------------------------------------------------
 // CG
 // ---------------------------------------------------------------------------------------------
-// cg.cpp:7-134 via kernel_interface.cpp:192-210: cg_init_u, cg_init_k, cg_init_others (+ r.p)
+// cg.cpp:7-134 via kernel_interface.cpp:192-210: cg_init_u, cg_init_k, cg_init_others (+ r.p) in ONE pass:
+// 64 B/cell (read energy, density; write u, kx, ky, w, r, p) instead of the 120 B of the three reference kernels.
+// u, the conductivity w and kx / ky of the neighbouring cells are recomputed from energy and density (same operations
+// on the same inputs: bit-identical to what the owning cell stores); every cell of every field ends up exactly as the
+// three-kernel sequence leaves it (p = r = 0 and w = conductivity outside the interior included).
 int tlk_cg_init(tl_chunk* c, int coefficient, double rx, double ry)
 {
     double *p = c->f[TL_FIELD_P], *r = c->f[TL_FIELD_R], *u = c->f[TL_FIELD_U], *w = c->f[TL_FIELD_W];
     double *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
     const double *den = c->f[TL_FIELD_DENSITY], *en = c->f[TL_FIELD_ENERGY1];
     const int x = c->g.x, y = c->g.y, hd = c->g.hd, pitch = c->g.pitch;
-    TL_TRY(launch_generic<0>(c, ALL_RANGE(c),
-                             [=] __device__(long i, int jj, int kk, double*) {
-                                 p[i] = 0.0;
-                                 r[i] = 0.0;
-                                 u[i] = en[i] * den[i];
-                                 if (jj > 0 && jj < y - 1 && kk > 0 && kk < x - 1)
-                                     w[i] = (coefficient == TL_CONDUCTIVITY) ? den[i] : 1.0 / den[i];
-                             },
-                             NoFin()));
-    TL_TRY(launch_generic<0>(c, hd, x - 1, hd, y - 1,
-                             [=] __device__(long i, int, int, double*) {
-                                 kx[i] = rx * (w[i - 1] + w[i]) / (2.0 * w[i - 1] * w[i]);
-                                 ky[i] = ry * (w[i - pitch] + w[i]) / (2.0 * w[i - pitch] * w[i]);
-                             },
-                             NoFin()));
+    const bool cond = (coefficient == TL_CONDUCTIVITY);
     return launch_generic<1>(
-        c, INTERIOR_RANGE(c),
-        [=] __device__(long i, int, int, double* acc) {
-            const double s = smvp(kx[i], kx[i + 1], ky[i], ky[i + pitch], u[i], u[i - 1], u[i + 1],
-                                  u[i - pitch], u[i + pitch]);
-            w[i] = s;
-            const double rv = u[i] - s;
-            r[i] = rv;
-            p[i] = rv;
-            acc[0] += rv * rv;
+        c, ALL_RANGE(c),
+        [=] __device__(long i, int jj, int kk, double* acc) {
+            auto wf = [&](double d) { return cond ? d : 1.0 / d; };       // cg.cpp:34-36 (cg_init_u)
+            const bool ring1 = jj > 0 && jj < y - 1 && kk > 0 && kk < x - 1;
+            const bool kcell = jj >= hd && jj < y - 1 && kk >= hd && kk < x - 1;
+            const bool interior = jj >= hd && jj < y - hd && kk >= hd && kk < x - hd;
+            const double dc = den[i];
+            const double uc = en[i] * dc;
+            u[i] = uc;
+            const double wc = wf(dc);
+            double kxc = 0.0, kyc = 0.0;
+            if (kcell) {                                                   // cg.cpp:61-63 (cg_init_k)
+                const double wl = wf(den[i - 1]), wd = wf(den[i - pitch]);
+                kxc = rx * (wl + wc) / (2.0 * wl * wc);
+                kyc = ry * (wd + wc) / (2.0 * wd * wc);
+                kx[i] = kxc;
+                ky[i] = kyc;
+            }
+            if (interior) {                                                // cg.cpp:96-127 (cg_init_others)
+                const double wr = wf(den[i + 1]), wu = wf(den[i + pitch]);
+                const double kxr = rx * (wc + wr) / (2.0 * wc * wr);       // kx[i + 1]
+                const double kyu = ry * (wc + wu) / (2.0 * wc * wu);       // ky[i + x]
+                const double sv = smvp(kxc, kxr, kyc, kyu, uc, en[i - 1] * den[i - 1], en[i + 1] * den[i + 1],
+                                       en[i - pitch] * den[i - pitch], en[i + pitch] * den[i + pitch]);
+                w[i] = sv;
+                const double rv = uc - sv;
+                r[i] = rv;
+                p[i] = rv;
+                acc[0] += rv * rv;
+            } else {
+                p[i] = 0.0;
+                r[i] = 0.0;
+                if (ring1) w[i] = wc;
+            }
         },
         [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
 }
@@ -518,21 +614,26 @@ static void tune_from_env()
     }
 }
 
-int tlk_tile_rows(const tl_chunk* c, int kernel)
+// Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read), but the tile count should sit
+// just under `ctas_per_sm` resident CTAs per SM so the whole grid is one balanced wave (profiles/tuning_r01.txt:
+// 4000x4000 at 8 CTAs per SM -> 55 rows, 1168 CTAs on 148 SMs).  ctas_per_sm is what the kernel's __launch_bounds__
+// guarantee: a grid sized for more CTAs than fit runs as one and a half waves.
+static int tall_tile_rows(const tl_chunk* c, int ctas_per_sm)
 {
-    tune_from_env();
-    if (g_rows[kernel] > 0) return g_rows[kernel];
-    if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
-    // Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read), but the tile
-    // count should sit just under 8 CTAs per SM so the whole grid is one balanced wave
-    // (profiles/tuning_r01.txt: 4000x4000 -> 55 rows, 1168 CTAs on 148 SMs).
     const int colb = (c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS;
-    int rowblocks = (8 * 148) / colb;
+    int rowblocks = (ctas_per_sm * 148) / colb;
     if (rowblocks < 1) rowblocks = 1;
     int rows = (c->ny + rowblocks - 1) / rowblocks;
     if (rows < 8) rows = 8;
     if (rows > 128) rows = 128;
     return rows;
+}
+int tlk_tile_rows(const tl_chunk* c, int kernel)
+{
+    tune_from_env();
+    if (g_rows[kernel] > 0) return g_rows[kernel];
+    if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
+    return tall_tile_rows(c, 8);
 }
 dim3 tlk_hot_grid(const tl_chunk* c, int rows)
 {
@@ -551,7 +652,7 @@ int tlk_hot_check(const tl_chunk* c, dim3 grid)
 // 32 B/cell of HBM traffic: read p, kx, ky; write w.  Rows j-1, j, j+1 of p and rows j, j+1 of ky
 // slide through registers, so every element is requested from L2 once per tile.
 template <int U, bool MULTI>
-__global__ void __launch_bounds__(TL_TPB)
+__global__ void __launch_bounds__(TL_TPB, 8)
 k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double* __restrict__ ky,
             double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev,
             const MultiCtx mc)
@@ -714,16 +815,15 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
                     acc[0] += rv[q].x * rv[q].x;
                     if (t.v1) acc[0] += rv[q].y * rv[q].y;
                     if constexpr (MULTI) { // fused loop: the updated r edge cells go to the neighbours' halo of r
-                        if (send_r_halo) edge_remote_store(g, mc, mc.nb_r, jb + q, rv[q], t);
+                        if (send_r_halo) edge_remote_store(g, mc, mc.nb_f, jb + q, rv[q], t);
                     }
                 }
             }
         }
     }
     if constexpr (MULTI) {
-        // only the edge tiles made remote halo stores: they must be visible system-wide before this CTA's ticket
-        const bool edge_tile = (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
-        if (send_r_halo && edge_tile) __threadfence_system();
+        // only the tiles on a face with a neighbour made remote halo stores: visible system-wide before this CTA's ticket
+        if (send_r_halo && tile_sends_halo(g, mc, t)) __threadfence_system();
     }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
@@ -735,7 +835,7 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
             // fenced its halo stores before its ticket)
             if (threadIdx.x < 32) rrn = mc_allsum_warp(mc, 1, tot[0], S);
             else if (send_r_halo && threadIdx.x < 64) {
-                mc_halo_handshake(mc, mc.nb_r, S, threadIdx.x - 32);
+                mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x - 32);
                 __syncwarp();
                 if (threadIdx.x == 32) stamp(S, it, 1, 3);
             }
@@ -762,6 +862,12 @@ int tlk_cg_calc_ur(tl_chunk* c, ScalMode mode, double alpha, bool rev, const Mul
     dim3 grid = tlk_hot_grid(c, rows);
     TL_TRY(tlk_hot_check(c, grid));
     RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
+    MultiCtx m = g_single_ctx;
+    if (mc && mc->num_ranks > 1) {
+        m = *mc;
+        tlk_set_travelling_field(c, &m, c->f[TL_FIELD_R]); // fused loop: r's edge cells go to the neighbours' halo of r
+    }
+    mc = &m;
 #define LAUNCH_UR(U)                                                                                       \
     if (mc && mc->num_ranks > 1)                                                                           \
         TL_CUDA(tl_launch(k_cg_calc_ur<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_U], \
@@ -814,7 +920,7 @@ __device__ __forceinline__ void p_halo_store(const Geo& g, double* p, long i, in
 template <int U, bool MULTI>
 __global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta_imm,
-            int rows, int rev, int halo_mask, double* __restrict__ d_betas, const MultiCtx mc)
+            int rows, int rev, int halo_mask, unsigned int* gcount, const MultiCtx mc)
 {
     constexpr bool multi = MULTI;
     double beta = beta_imm;
@@ -849,8 +955,8 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
     if (!MULTI && !t.v0) return;
     if (t.v0) load_r(t.j0);
     if (t.v0) {
-        const bool edge_tile = (halo_mask || multi) && (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 ||
-                                                        blockIdx.x == gridDim.x - 1);
+        const bool edge_tile = (halo_mask || multi) && (t.j0 == g.hd || t.j1 == g.y - g.hd || t.tile % gridDim.x == 0 ||
+                                                        t.tile % gridDim.x == gridDim.x - 1);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             if (jb != t.j0) load_batch(jb);
 #pragma unroll
@@ -866,7 +972,7 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
                 for (int q = 0; q < U; ++q)
                     if (jb + q < t.j1) {
                         if (halo_mask) p_halo_store(g, p, i + q * pitch, jb + q, pv[q], t, halo_mask);
-                        if (multi) edge_remote_store(g, mc, mc.nb_p, jb + q, pv[q], t);
+                        if (multi) edge_remote_store(g, mc, mc.nb_f, jb + q, pv[q], t);
                     }
             }
         }
@@ -875,19 +981,9 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
         // Every CTA makes its remote halo stores visible system-wide before taking its ticket; the last CTA to finish
         // releases the neighbours' per-face flags and acquires its own: when this kernel completes, the halo of p that
         // the next matvec reads is in place (what halo_update_driver.c:22 provides in the reference).
-        __shared__ int s_last;
-        const bool edge_cta = (t.j0 == g.hd || t.j1 == g.y - g.hd || blockIdx.x == 0 || blockIdx.x == gridDim.x - 1);
-        if (edge_cta) __threadfence_system(); // only edge tiles made remote stores
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned int tk = atomicAdd(&S->counter[1], 1u);
-            s_last = (tk == gridDim.x * gridDim.y - 1);
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < 32) {
-            if (threadIdx.x == 0) S->counter[1] = 0u;
-            __threadfence();
-            mc_halo_handshake(mc, mc.nb_p, S, threadIdx.x);
+        if (tile_sends_halo(g, mc, t)) __threadfence_system();
+        if (grid_last_cta(gcount, &S->counter[1], t.tile, t.ntiles) && threadIdx.x < 32) {
+            mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x);
             __syncwarp();
             if (threadIdx.x == 0) stamp(S, it, 2, 3);
         }
@@ -904,20 +1000,30 @@ int tlk_external_mask(const tl_chunk* c)
     return mask;
 }
 
+void tlk_set_travelling_field(const tl_chunk* c, MultiCtx* mc, const double* buf)
+{
+    const size_t slot = (size_t)(buf - c->slab) / c->field_elems;
+    for (int f = 0; f < 4; ++f)
+        mc->nb_f[f] = c->nb_slab[f] ? c->nb_slab[f] + slot * c->nb_field_elems[f] : nullptr;
+}
+
 int tlk_cg_calc_p(tl_chunk* c, ScalMode mode, double beta, bool rev, bool fuse_halo, const MultiCtx* mc, bool pdl)
 {
     const int rows = tlk_tile_rows(c, TUNE_P);
     dim3 grid = tlk_hot_grid(c, rows);
     const int mask = fuse_halo ? tlk_external_mask(c) : 0;
+    MultiCtx m = g_single_ctx;
+    if (mc && mc->num_ranks > 1) {
+        m = *mc;
+        tlk_set_travelling_field(c, &m, c->f[TL_FIELD_P]); // p's edge cells go to the neighbours' halo of p
+    }
 #define LAUNCH_P(U)                                                                                         \
-    if (mc && mc->num_ranks > 1)                                                                            \
+    if (m.num_ranks > 1)                                                                                    \
         TL_CUDA(tl_launch(k_cg_calc_p<U, true>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],  \
-                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->d_betas,      \
-                          *mc));                                                                              \
+                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->gcount, m));  \
     else                                                                                                    \
         TL_CUDA(tl_launch(k_cg_calc_p<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P], \
-                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->d_betas,      \
-                          g_single_ctx))
+                          c->f[TL_FIELD_R], c->scal, (int)mode, beta, rows, rev ? 1 : 0, mask, c->gcount, m))
     switch (g_batch[TUNE_P]) {
     case 1: LAUNCH_P(1); break;
     case 2: LAUNCH_P(2); break;
@@ -1066,11 +1172,6 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
     const int rows = tlk_tile_rows(c, TUNE_PW);
     dim3 grid = tlk_hot_grid(c, rows);
     TL_TRY(tlk_hot_check(c, grid));
-    if (!c->p2) {
-        TL_CUDA(cudaMalloc((void**)&c->p2, c->field_elems * sizeof(double)));
-        c->p2_alloc = c->p2;
-        TL_CUDA(cudaMemsetAsync(c->p2, 0, c->field_elems * sizeof(double), c->stream));
-    }
     if (tlk_pw_uses_bulk()) { // optional: TMA bulk-copy row pipeline, persistent CTAs (tl_bulk.cu); bit-identical results
         TL_TRY(tlk_cg_calc_pw_bulk(c, rev, mc, rows, pdl));
         double* tmp = c->f[TL_FIELD_P];
@@ -1119,106 +1220,147 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
 // would have put in the halo), so no halo kernel runs between iterations on a single chunk; internal
 // faces read the exchanged halo.  Same operations in the same order as the two reference kernels:
 // results are bit-identical.  `w` (= A u) is never read in the Chebyshev phase and is not stored here.
+// Several ranks (MULTI): the thread that owns an edge cell of an internal face also stores the updated operand into the
+// neighbour's halo cell of ITS output buffer (both ranks swap buffers in lockstep), and the last CTA of the grid
+// hand-shakes with the neighbours -- the exchange of halo_update_driver.c for {u} / {sd}, depth 1, inside the kernel.
+// NORM: the kernel also returns sum r.r over the interior (all ranks), i.e. the calculate_2norm(r) that
+// cheby_driver.c:128-133 / ppcg_driver.c:136-141 run after it, without another pass over r.
 enum { MODE_CHEBY = 0, MODE_PPCG = 1 };
-template <int MODE, int U>
-__global__ void __launch_bounds__(TL_TPB)
+#define TL_FS_CTAS_PER_SM 5 // 102 registers: the U = 2 load batch of five streams needs ~100
+template <int MODE, int U, bool MULTI, bool NORM>
+__global__ void __launch_bounds__(TL_TPB, TL_FS_CTAS_PER_SM)
 k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_out, double* __restrict__ f1,
                 const double* f2_in, double* f2_out, const double* __restrict__ kx, const double* __restrict__ ky,
-                double alpha, double beta, int rows, int rev, int ext_mask)
+                double alpha, double beta, int rows, int rev, int ext_mask, RedArgs ra, const MultiCtx mc)
 {
     // MODE_CHEBY: f1 = p (in/out), f2_in = u0 (read), f2_out = r (written)
     // MODE_PPCG : f1 = r (in/out), f2_in = f2_out = u (in/out)
     const HotTile t = hot_tile(g, rows, rev);
-    if (!t.v0) return;
-    const long pitch = g.pitch;
-    const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
-    const int dl = ((ext_mask & 1) && t.kk == klo) ? 0 : -1;         // left neighbour of cell 0 (mirrored: itself)
-    const int dr = ((ext_mask & 2) && t.kk + 1 == khi) ? 1 : 2;      // right neighbour of cell 1
-    const bool mir_r0 = (ext_mask & 2) && t.kk == khi;               // cell 0 is the last column
-    long i = t.i;
-    const long im = ((ext_mask & 4) && t.j0 == jlo) ? i : i - pitch;
-    double2 am = ld2_ro(a_in + im);
-    double2 ac = ld2_ro(a_in + i);
-    double al = __ldg(a_in + i + dl), ar = __ldg(a_in + i + dr);
-    double2 kyc = ld2_ro(ky + i);
-    for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-        double2 an[U], kyn[U], kxc[U], x1[U], x2[U];
-        double kxr[U], aln[U], arn[U];
+    double acc[1] = {0.0};
+    if (t.v0) {
+        const long pitch = g.pitch;
+        const int klo = g.hd, khi = g.x - g.hd - 1, jlo = g.hd, jhi = g.y - g.hd - 1;
+        const int dl = ((ext_mask & 1) && t.kk == klo) ? 0 : -1;         // left neighbour of cell 0 (mirrored: itself)
+        const int dr = ((ext_mask & 2) && t.kk + 1 == khi) ? 1 : 2;      // right neighbour of cell 1
+        const bool mir_r0 = (ext_mask & 2) && t.kk == khi;               // cell 0 is the last column
+        [[maybe_unused]] const bool sends = MULTI && tile_sends_halo(g, mc, t);
+        long i = t.i;
+        const long im = ((ext_mask & 4) && t.j0 == jlo) ? i : i - pitch;
+        double2 am = ld2_ro(a_in + im);
+        double2 ac = ld2_ro(a_in + i);
+        double al = __ldg(a_in + i + dl), ar = __ldg(a_in + i + dr);
+        double2 kyc = ld2_ro(ky + i);
+        for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
+            double2 an[U], kyn[U], kxc[U], x1[U], x2[U];
+            double kxr[U], aln[U], arn[U];
 #pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (jb + q < t.j1) {
-                const long iq = i + q * pitch;
-                const long in = ((ext_mask & 8) && jb + q == jhi) ? iq : iq + pitch;
-                an[q] = ld2_ro(a_in + in);
-                aln[q] = __ldg(a_in + in + dl);
-                arn[q] = __ldg(a_in + in + dr);
-                kyn[q] = ld2_ro(ky + iq + pitch);
-                kxc[q] = ld2_ro(kx + iq);
-                kxr[q] = __ldg(kx + iq + 2);
-                x1[q] = ld2(f1 + iq);
-                x2[q] = ld2(f2_in + iq);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (jb + q < t.j1) {
-                const long iq = i + q * pitch;
-                double2 sv;
-                sv.x = smvp(kxc[q].x, kxc[q].y, kyc.x, kyn[q].x, ac.x, al, mir_r0 ? ac.x : ac.y, am.x, an[q].x);
-                sv.y = smvp(kxc[q].y, kxr[q], kyc.y, kyn[q].y, ac.y, ac.x, ar, am.y, an[q].y);
-                double2 o1, o2, ao;
-                if (MODE == MODE_CHEBY) {
-                    // x1 = p, x2 = u0:  r = u0 - s ; p = alpha p + beta r ; u' = u + p
-                    o2.x = x2[q].x - sv.x;
-                    o2.y = x2[q].y - sv.y;
-                    o1.x = alpha * x1[q].x + beta * o2.x;
-                    o1.y = alpha * x1[q].y + beta * o2.y;
-                    ao.x = ac.x + o1.x;
-                    ao.y = ac.y + o1.y;
-                } else {
-                    // x1 = r, x2 = u:  r -= s ; u += sd ; sd' = alpha sd + beta r
-                    o1.x = x1[q].x - sv.x;
-                    o1.y = x1[q].y - sv.y;
-                    o2.x = x2[q].x + ac.x;
-                    o2.y = x2[q].y + ac.y;
-                    ao.x = alpha * ac.x + beta * o1.x;
-                    ao.y = alpha * ac.y + beta * o1.y;
+            for (int q = 0; q < U; ++q) {
+                if (jb + q < t.j1) {
+                    const long iq = i + q * pitch;
+                    const long in = ((ext_mask & 8) && jb + q == jhi) ? iq : iq + pitch;
+                    an[q] = ld2_ro(a_in + in);
+                    aln[q] = __ldg(a_in + in + dl);
+                    arn[q] = __ldg(a_in + in + dr);
+                    kyn[q] = ld2_ro(ky + iq + pitch);
+                    kxc[q] = ld2_ro(kx + iq);
+                    kxr[q] = __ldg(kx + iq + 2);
+                    x1[q] = ld2(f1 + iq);
+                    x2[q] = ld2(f2_in + iq);
                 }
-                st_pair(f1 + iq, o1, t.v1);
-                st_pair(f2_out + iq, o2, t.v1);
-                st_pair(a_out + iq, ao, t.v1);
-                am = ac; ac = an[q]; kyc = kyn[q]; al = aln[q]; ar = arn[q];
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (jb + q < t.j1) {
+                    const long iq = i + q * pitch;
+                    double2 sv;
+                    sv.x = smvp(kxc[q].x, kxc[q].y, kyc.x, kyn[q].x, ac.x, al, mir_r0 ? ac.x : ac.y, am.x, an[q].x);
+                    sv.y = smvp(kxc[q].y, kxr[q], kyc.y, kyn[q].y, ac.y, ac.x, ar, am.y, an[q].y);
+                    double2 o1, o2, ao, rn;
+                    if (MODE == MODE_CHEBY) {
+                        // x1 = p, x2 = u0:  r = u0 - s ; p = alpha p + beta r ; u' = u + p
+                        o2.x = x2[q].x - sv.x;
+                        o2.y = x2[q].y - sv.y;
+                        o1.x = alpha * x1[q].x + beta * o2.x;
+                        o1.y = alpha * x1[q].y + beta * o2.y;
+                        ao.x = ac.x + o1.x;
+                        ao.y = ac.y + o1.y;
+                        rn = o2;
+                    } else {
+                        // x1 = r, x2 = u:  r -= s ; u += sd ; sd' = alpha sd + beta r
+                        o1.x = x1[q].x - sv.x;
+                        o1.y = x1[q].y - sv.y;
+                        o2.x = x2[q].x + ac.x;
+                        o2.y = x2[q].y + ac.y;
+                        ao.x = alpha * ac.x + beta * o1.x;
+                        ao.y = alpha * ac.y + beta * o1.y;
+                        rn = o1;
+                    }
+                    st_pair(f1 + iq, o1, t.v1);
+                    st_pair(f2_out + iq, o2, t.v1);
+                    st_pair(a_out + iq, ao, t.v1);
+                    if constexpr (NORM) {
+                        acc[0] += rn.x * rn.x;
+                        if (t.v1) acc[0] += rn.y * rn.y;
+                    }
+                    if constexpr (MULTI) {
+                        if (sends) edge_remote_store(g, mc, mc.nb_f, jb + q, ao, t);
+                    }
+                    am = ac; ac = an[q]; kyc = kyn[q]; al = aln[q]; ar = arn[q];
+                }
             }
         }
     }
-}
-
-static int alt_buffer(tl_chunk* c, int field)
-{
-    if (!c->alt_alloc[field]) {
-        TL_CUDA(cudaMalloc((void**)&c->alt_alloc[field], c->field_elems * sizeof(double)));
-        TL_CUDA(cudaMemsetAsync(c->alt_alloc[field], 0, c->field_elems * sizeof(double), c->stream));
-        c->alt[field] = c->alt_alloc[field];
+    if constexpr (MULTI) {
+        if (tile_sends_halo(g, mc, t)) __threadfence_system(); // remote halo stores visible before this CTA's ticket
     }
-    return TL_OK;
+    if constexpr (NORM) {
+        double tot[1];
+        if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+            double nrm = tot[0];
+            if constexpr (MULTI) {
+                if (threadIdx.x < 32) nrm = mc_allsum_warp(mc, 1, tot[0], ra.S); // sum_over_ranks, cheby_driver.c:132
+                else if (threadIdx.x < 64) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x - 32);
+            }
+            if (threadIdx.x == 0) ra.S->sums[0] = nrm;
+        }
+    } else if constexpr (MULTI) {
+        if (grid_last_cta(ra.gcount, &ra.S->counter[1], t.tile, t.ntiles) && threadIdx.x < 32)
+            mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x);
+    }
 }
 
 // Runs one fused iteration and swaps the operand's two buffers (field = TL_FIELD_U or TL_FIELD_SD).
-static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta)
+static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta, const MultiCtx* mc, bool norm)
 {
     const int field = (mode == MODE_CHEBY) ? TL_FIELD_U : TL_FIELD_SD;
-    TL_TRY(alt_buffer(c, field));
-    const int rows = tlk_tile_rows(c, TUNE_W);
+    tune_from_env();
+    const int rows = g_rows[TUNE_W] > 0 ? g_rows[TUNE_W] : tall_tile_rows(c, TL_FS_CTAS_PER_SM);
     dim3 grid = tlk_hot_grid(c, rows);
+    TL_TRY(tlk_hot_check(c, grid));
     const int mask = tlk_external_mask(c);
-    if (mode == MODE_CHEBY)
-        k_fused_stencil<MODE_CHEBY, 2><<<grid, TL_TPB, 0, c->stream>>>(
-            c->g, c->f[TL_FIELD_U], c->alt[TL_FIELD_U], c->f[TL_FIELD_P], c->f[TL_FIELD_U0], c->f[TL_FIELD_R],
-            c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask);
-    else
-        k_fused_stencil<MODE_PPCG, 2><<<grid, TL_TPB, 0, c->stream>>>(
-            c->g, c->f[TL_FIELD_SD], c->alt[TL_FIELD_SD], c->f[TL_FIELD_R], c->f[TL_FIELD_U], c->f[TL_FIELD_U],
-            c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask);
+    RedArgs ra{c->partials, c->gpartials, c->gcount, c->partial_cap, c->gpartial_cap, c->scal};
+    MultiCtx m = g_single_ctx;
+    const bool multi = mc && mc->num_ranks > 1;
+    if (multi) {
+        m = *mc;
+        tlk_set_travelling_field(c, &m, c->alt[field]); // the neighbours' copy of the buffer this launch writes
+    }
+#define LAUNCH_FS(MODE, MULTI, NORM)                                                                            \
+    do {                                                                                                        \
+        if (MODE == MODE_CHEBY)                                                                                 \
+            k_fused_stencil<MODE_CHEBY, 2, MULTI, NORM><<<grid, TL_TPB, 0, c->stream>>>(                        \
+                c->g, c->f[TL_FIELD_U], c->alt[TL_FIELD_U], c->f[TL_FIELD_P], c->f[TL_FIELD_U0], c->f[TL_FIELD_R], \
+                c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask, ra, m);                       \
+        else                                                                                                    \
+            k_fused_stencil<MODE_PPCG, 2, MULTI, NORM><<<grid, TL_TPB, 0, c->stream>>>(                         \
+                c->g, c->f[TL_FIELD_SD], c->alt[TL_FIELD_SD], c->f[TL_FIELD_R], c->f[TL_FIELD_U], c->f[TL_FIELD_U], \
+                c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], alpha, beta, rows, 0, mask, ra, m);                       \
+    } while (0)
+    if (multi && norm) LAUNCH_FS(mode, true, true);
+    else if (multi) LAUNCH_FS(mode, true, false);
+    else if (norm) LAUNCH_FS(mode, false, true);
+    else LAUNCH_FS(mode, false, false);
+#undef LAUNCH_FS
     ++g_tl_launches;
     TL_CUDA(cudaGetLastError());
     double* tmp = c->f[field];
@@ -1226,8 +1368,14 @@ static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta
     c->alt[field] = tmp;
     return TL_OK;
 }
-int tlk_cheby_fused(tl_chunk* c, double alpha, double beta) { return launch_fused_stencil(c, MODE_CHEBY, alpha, beta); }
-int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta) { return launch_fused_stencil(c, MODE_PPCG, alpha, beta); }
+int tlk_cheby_fused(tl_chunk* c, double alpha, double beta, const MultiCtx* mc, bool norm)
+{
+    return launch_fused_stencil(c, MODE_CHEBY, alpha, beta, mc, norm);
+}
+int tlk_ppcg_fused(tl_chunk* c, double alpha, double beta, const MultiCtx* mc, bool norm)
+{
+    return launch_fused_stencil(c, MODE_PPCG, alpha, beta, mc, norm);
+}
 
 // Puts a double-buffered field back into its slab position (copy if it currently lives in the
 // alternate buffer), so that slab-relative peer mappings and later phases see it where they expect.
@@ -1284,16 +1432,23 @@ int tlk_cheby_calc_u(tl_chunk* c)
 {
     double* u = c->f[TL_FIELD_U];
     const double* p = c->f[TL_FIELD_P];
-    return launch_generic<0>(c, INTERIOR_RANGE(c),
-                             [=] __device__(long i, int, int, double*) { u[i] += p[i]; }, NoFin());
+    return launch_vec<0, 4, V2>(c, INTERIOR_RANGE(c),
+                                [=] __device__(long i, int, int) { return V2{ld2(u + i), ld2(p + i)}; },
+                                [=] __device__(const V2& v, long i, int, int, bool v0, bool v1, double*) {
+                                    st_mask(u + i, make_double2(v.a.x + v.b.x, v.a.y + v.b.y), v0, v1);
+                                },
+                                NoFin());
 }
 // ppcg.cpp:7-31
 int tlk_ppcg_init(tl_chunk* c, double theta)
 {
     double* sd = c->f[TL_FIELD_SD];
     const double* r = c->f[TL_FIELD_R];
-    return launch_generic<0>(c, INTERIOR_RANGE(c),
-                             [=] __device__(long i, int, int, double*) { sd[i] = r[i] / theta; }, NoFin());
+    return launch_vec<0, 4, V1>(c, INTERIOR_RANGE(c), [=] __device__(long i, int, int) { return V1{ld2(r + i)}; },
+                                [=] __device__(const V1& v, long i, int, int, bool v0, bool v1, double*) {
+                                    st_mask(sd + i, make_double2(v.a.x / theta, v.a.y / theta), v0, v1);
+                                },
+                                NoFin());
 }
 // ppcg.cpp:34-66
 int tlk_ppcg_calc_ur(tl_chunk* c)
@@ -1315,9 +1470,13 @@ int tlk_ppcg_calc_sd(tl_chunk* c, double alpha, double beta)
 {
     double* sd = c->f[TL_FIELD_SD];
     const double* r = c->f[TL_FIELD_R];
-    return launch_generic<0>(c, INTERIOR_RANGE(c),
-                             [=] __device__(long i, int, int, double*) { sd[i] = alpha * sd[i] + beta * r[i]; },
-                             NoFin());
+    return launch_vec<0, 4, V2>(c, INTERIOR_RANGE(c),
+                                [=] __device__(long i, int, int) { return V2{ld2(sd + i), ld2(r + i)}; },
+                                [=] __device__(const V2& v, long i, int, int, bool v0, bool v1, double*) {
+                                    st_mask(sd + i, make_double2(alpha * v.a.x + beta * v.b.x, alpha * v.a.y + beta * v.b.y),
+                                            v0, v1);
+                                },
+                                NoFin());
 }
 // jacobi.cpp:7-54
 int tlk_jacobi_init(tl_chunk* c, int coefficient, double rx, double ry)
@@ -1345,20 +1504,41 @@ int tlk_jacobi_init(tl_chunk* c, int coefficient, double rx, double ry)
         NoFin());
 }
 // kernel_interface.cpp:287-300: jacobi_copy_u (all cells) then jacobi_iterate (jacobi.cpp:57-117)
+struct VJac {
+    double2 u0, rc, rd, ru, kx, kyc, kyu;
+    double rl, rr, kxr;
+};
 int tlk_jacobi_iterate(tl_chunk* c)
 {
     TL_TRY(tlk_copy_field(c, TL_FIELD_R, TL_FIELD_U, false));
     double* u = c->f[TL_FIELD_U];
     const double *u0 = c->f[TL_FIELD_U0], *r = c->f[TL_FIELD_R], *kx = c->f[TL_FIELD_KX], *ky = c->f[TL_FIELD_KY];
     const int pitch = c->g.pitch;
-    return launch_generic<1>(
+    return launch_vec<1, 2, VJac>(
         c, INTERIOR_RANGE(c),
-        [=] __device__(long i, int, int, double* acc) {
-            const double v = (u0[i] + (kx[i + 1] * r[i + 1] + kx[i] * r[i - 1]) +
-                              (ky[i + pitch] * r[i + pitch] + ky[i] * r[i - pitch])) /
-                             (1.0 + (kx[i] + kx[i + 1]) + (ky[i] + ky[i + pitch]));
-            u[i] = v;
-            acc[0] += fabs(v - r[i]);
+        [=] __device__(long i, int, int) {
+            VJac v;
+            v.u0 = ld2(u0 + i);
+            v.rc = ld2(r + i);
+            v.rd = ld2(r + i - pitch);
+            v.ru = ld2(r + i + pitch);
+            v.kx = ld2(kx + i);
+            v.kyc = ld2(ky + i);
+            v.kyu = ld2(ky + i + pitch);
+            v.rl = r[i - 1];
+            v.rr = r[i + 2];
+            v.kxr = kx[i + 2];
+            return v;
+        },
+        [=] __device__(const VJac& v, long i, int, int, bool v0, bool v1, double* acc) {
+            double2 o;
+            o.x = (v.u0.x + (v.kx.y * v.rc.y + v.kx.x * v.rl) + (v.kyu.x * v.ru.x + v.kyc.x * v.rd.x)) /
+                  (1.0 + (v.kx.x + v.kx.y) + (v.kyc.x + v.kyu.x));
+            o.y = (v.u0.y + (v.kxr * v.rr + v.kx.y * v.rc.x) + (v.kyu.y * v.ru.y + v.kyc.y * v.rd.y)) /
+                  (1.0 + (v.kx.y + v.kxr) + (v.kyc.y + v.kyu.y));
+            st_mask(u + i, o, v0, v1);
+            if (v0) acc[0] += fabs(o.x - v.rc.x);
+            if (v1) acc[0] += fabs(o.y - v.rc.y);
         },
         [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
 }
@@ -1380,15 +1560,22 @@ int tlk_calculate_residual(tl_chunk* c)
 int tlk_calculate_2norm(tl_chunk* c, int field)
 {
     const double* b = c->f[field];
-    return launch_generic<1>(c, INTERIOR_RANGE(c),
-                             [=] __device__(long i, int, int, double* acc) { acc[0] += b[i] * b[i]; },
-                             [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
+    return launch_vec<1, 4, V1>(c, INTERIOR_RANGE(c), [=] __device__(long i, int, int) { return V1{ld2(b + i)}; },
+                                [=] __device__(const V1& v, long, int, int, bool v0, bool v1, double* acc) {
+                                    if (v0) acc[0] += v.a.x * v.a.x;
+                                    if (v1) acc[0] += v.a.y * v.a.y;
+                                },
+                                [=] __device__(const double* t, DevScal* S) { S->sums[0] = t[0]; });
 }
 // solver_methods.cpp:120-145
 int tlk_finalise(tl_chunk* c)
 {
     double* en = c->f[TL_FIELD_ENERGY1];
     const double *u = c->f[TL_FIELD_U], *den = c->f[TL_FIELD_DENSITY];
-    return launch_generic<0>(c, INTERIOR_RANGE(c),
-                             [=] __device__(long i, int, int, double*) { en[i] = u[i] / den[i]; }, NoFin());
+    return launch_vec<0, 4, V2>(c, INTERIOR_RANGE(c),
+                                [=] __device__(long i, int, int) { return V2{ld2(u + i), ld2(den + i)}; },
+                                [=] __device__(const V2& v, long i, int, int, bool v0, bool v1, double*) {
+                                    st_mask(en + i, make_double2(v.a.x / v.b.x, v.a.y / v.b.y), v0, v1);
+                                },
+                                NoFin());
 }

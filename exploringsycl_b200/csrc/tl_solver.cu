@@ -159,6 +159,9 @@ static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double 
     }
     int nb = 0, n_pw = 0;
     bool done = (enq >= stop_iters);
+    // TL_DBG_NOSEND=1 (timing experiments only, WRONG results): the fused loop keeps r's halo at home
+    static const bool dbg_nosend = getenv("TL_DBG_NOSEND") && getenv("TL_DBG_NOSEND")[0] == '1';
+    const bool send_r = multi && !dbg_nosend;
     while (!done) {
         const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
         for (int it = 0; it < todo; ++it) {
@@ -178,7 +181,7 @@ static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double 
                     TL_TRY(tlk_cg_calc_pw(c, false, mcp, pdl));
                     ++n_pw;
                 }
-                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, mcp, multi, pdl));
+                TL_TRY(tlk_cg_calc_ur(c, SCAL_DEV, 0.0, true, mcp, send_r, pdl));
                 *launches += 2;
             }
         }
@@ -465,6 +468,16 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
     int num_cheby_iters = 0, est_iterations = 0;
     double theta = 0.0;
     const bool fused = o->fuse_p_into_w != 0;
+    // One-pass kernel on several ranks: u's edge cells travel inside the kernel (NVLink peer stores + per-face
+    // hand-shake in its last CTA) instead of a halo_update_driver round of four launches per iteration.
+    const bool inkernel = fused && multi && use_resident_multi(c, k);
+    MultiCtx mc = c->mc;
+    const MultiCtx* mcp = nullptr;
+    int n_seq = 0;
+    if (inkernel) {
+        mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
+        mcp = &mc;
+    }
     if (!ended) {
         for (; tt < o->max_iters; ++tt) {
             num_cheby_iters++;
@@ -487,15 +500,23 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
                 calc_2norm = (num_cheby_iters >= est_iterations) && ((tt + 1) % 10 == 0);
             }
             // cheby_main_step_driver, cheby_driver.c:110-143
-            if (fused) { // one pass: cheby_iterate + cheby_calc_u, u double buffered
-                TL_TRY(tlk_cheby_fused(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters]));
+            if (fused) {
+                // one pass: cheby_iterate + cheby_calc_u (u double buffered) + on the sampled iterations the 2-norm of r
+                mc.tl = n_seq++;
+                TL_TRY(tlk_cheby_fused(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters], mcp,
+                                       calc_2norm));
                 launches += 1;
+                if (calc_2norm) {
+                    TL_TRY(tl_fetch_scal(c));
+                    error = c->scal_h->sums[0];
+                    if (!inkernel) TL_TRY(sum_ranks(k, &error)); // in-kernel: already the sum over all ranks
+                }
             } else {
                 TL_TRY(tlk_cheby_iterate(c, c->cheby_alphas[num_cheby_iters], c->cheby_betas[num_cheby_iters]));
                 TL_TRY(tlk_cheby_calc_u(c));
                 launches += 2;
+                if (calc_2norm) TL_TRY(norm2(c, k, TL_FIELD_R, &error));
             }
-            if (calc_2norm) TL_TRY(norm2(c, k, TL_FIELD_R, &error));
             if (num_cheby_iters == 1) {
                 // cheby_calc_est_iterations, cheby_driver.c:146-160 (float logf/roundf as written)
                 const double cn = info->eigmax / info->eigmin;
@@ -503,14 +524,15 @@ static int cheby_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double 
                 const double gamm = (sqrt(cn) - 1.0) / (sqrt(cn) + 1.0);
                 est_iterations = (int)roundf(logf(it_alpha) / (2.0 * logf(gamm)));
             }
-            // On one chunk the fused kernel applies the reflective boundary by mirroring: u's halo is only
-            // materialised once, after the loop.
-            if (!(fused && !multi)) TL_TRY(tl_halo_update(c, k, fields, 1));
+            // The one-pass kernel applies the reflective boundary by mirroring and (several ranks) delivers the
+            // neighbours' halo itself: u's halo is only materialised once, after the loop.
+            if (!fused || (multi && !inkernel)) TL_TRY(tl_halo_update(c, k, fields, 1));
             if (fabs(error) < o->eps) break;
         }
+        if (inkernel) tlc_resident_seq_advance(k, n_seq); // same count on every rank: `error` is a global sum
         if (fused) {
             TL_TRY(tlk_field_home(c, TL_FIELD_U));
-            if (!multi && num_cheby_iters > 0) TL_TRY(tl_halo_update(c, k, fields, 1));
+            if ((!multi || inkernel) && num_cheby_iters > 0) TL_TRY(tl_halo_update(c, k, fields, 1));
         }
     }
     info->iters_a = tt - num_cheby_iters + 1; // cheby_driver.c:73
@@ -537,6 +559,15 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
     int num_ppcg_iters = 0;
     double theta = 0.0;
     const bool fused = o->fuse_p_into_w != 0;
+    // see cheby_solve: sd's edge cells travel inside the one-pass kernel
+    const bool inkernel = fused && multi && use_resident_multi(c, k);
+    MultiCtx mc = c->mc;
+    const MultiCtx* mcp = nullptr;
+    int n_seq = 0;
+    if (inkernel) {
+        mc.sbase = mc.hbase = tlc_resident_seq_advance(k, 0);
+        mcp = &mc;
+    }
     if (!ended) {
         for (; tt < o->max_iters; ++tt) {
             num_ppcg_iters++;
@@ -562,21 +593,32 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
             TL_TRY(tlk_ppcg_init(c, theta));
             fields_reset(fields);
             fields[TL_FIELD_SD] = 1;
-            for (int pp = 0; pp < o->ppcg_inner_steps; ++pp) {
-                if (fused) { // one pass: ppcg_calc_ur + ppcg_calc_sd, sd double buffered, boundary by mirroring
-                    if (multi) TL_TRY(tl_halo_update(c, k, fields, 1));
-                    TL_TRY(tlk_ppcg_fused(c, c->cheby_alphas[pp], c->cheby_betas[pp]));
-                } else {
+            double rrn = 0.0;
+            if (fused && o->ppcg_inner_steps > 0) {
+                // one pass per inner step: ppcg_calc_ur + ppcg_calc_sd, sd double buffered, boundary by mirroring; the
+                // last step also returns the 2-norm of r (:136-141).  Several ranks: one exchange of sd after
+                // ppcg_init, then every step delivers the next step's halo itself.
+                if (multi) TL_TRY(tl_halo_update(c, k, fields, 1));
+                for (int pp = 0; pp < o->ppcg_inner_steps; ++pp) {
+                    const bool last = (pp == o->ppcg_inner_steps - 1);
+                    if (multi && !inkernel && pp > 0) TL_TRY(tl_halo_update(c, k, fields, 1));
+                    mc.tl = n_seq++;
+                    TL_TRY(tlk_ppcg_fused(c, c->cheby_alphas[pp], c->cheby_betas[pp], mcp, last));
+                }
+                TL_TRY(tl_fetch_scal(c));
+                rrn = c->scal_h->sums[0];
+                if (!inkernel) TL_TRY(sum_ranks(k, &rrn));
+            } else {
+                for (int pp = 0; pp < o->ppcg_inner_steps; ++pp) {
                     TL_TRY(tl_halo_update(c, k, fields, 1));
                     TL_TRY(tlk_ppcg_calc_ur(c));
                     TL_TRY(tlk_ppcg_calc_sd(c, c->cheby_alphas[pp], c->cheby_betas[pp]));
                 }
+                TL_TRY(norm2(c, k, TL_FIELD_R, &rrn));
             }
             launches += 3 + (fused ? 1 : 2) * o->ppcg_inner_steps;
             fields_reset(fields);
             fields[TL_FIELD_P] = 1;
-            double rrn = 0.0;
-            TL_TRY(norm2(c, k, TL_FIELD_R, &rrn));
             const double beta = rrn / rro;
             TL_TRY(tlk_cg_calc_p(c, SCAL_IMM, beta, false, false));
             error = rrn;
@@ -584,6 +626,7 @@ static int ppcg_solve(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, double r
             TL_TRY(tl_halo_update(c, k, fields, 1));
             if (fabs(error) < o->eps) break;
         }
+        if (inkernel) tlc_resident_seq_advance(k, n_seq);
     }
     if (fused) TL_TRY(tlk_field_home(c, TL_FIELD_SD));
     info->iters_a = tt - num_ppcg_iters + 1; // ppcg_driver.c:59

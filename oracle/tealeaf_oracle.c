@@ -97,12 +97,14 @@ static double block128(double* t) /* 128 per-thread values -> CTA value */
     double w0 = butterfly32(t), w1 = butterfly32(t + 32), w2 = butterfly32(t + 64), w3 = butterfly32(t + 96);
     return (w0 + w1) + (w2 + w3);
 }
-enum { SUM_GENERIC = 0, SUM_HOT_W = 1, SUM_HOT_UR = 2 };
+enum { SUM_GENERIC = 0, SUM_HOT_W = 1, SUM_HOT_UR = 2, SUM_GENERIC_ALL = 3, SUM_HOT_FS = 4 };
 static int gpu_tile_rows(int kind, int nx, int ny)
 {
-    if (kind != SUM_HOT_W) return 8;
+    if (kind != SUM_HOT_W && kind != SUM_HOT_FS) return 8;
+    /* one balanced wave of tall tiles: 8 resident CTAs per SM for the CG matvec kernels, 5 for the one-pass
+     * Chebyshev / PPCG kernels (TL_FS_CTAS_PER_SM in tl_kernels.cu) */
     int colb = (nx + 255) / 256;
-    int rowblocks = (8 * 148) / colb;
+    int rowblocks = ((kind == SUM_HOT_FS ? 5 : 8) * 148) / colb;
     if (rowblocks < 1) rowblocks = 1;
     int rows = (ny + rowblocks - 1) / rowblocks;
     if (rows < 8) rows = 8;
@@ -111,8 +113,11 @@ static int gpu_tile_rows(int kind, int nx, int ny)
 }
 static double gpu_order_sum(const double* val, int x, int y, int hd, int kind)
 {
-    const int nx = x - 2 * hd, ny = y - 2 * hd;
-    const int cpt = (kind == SUM_GENERIC) ? 1 : 2, tile_cols = 128 * cpt;
+    /* SUM_GENERIC_ALL: the one-pass cg_init kernel runs over ALL cells (tiles start at cell (0,0); the cells outside
+     * the interior contribute 0.0); the other kinds tile the interior. */
+    const int o = (kind == SUM_GENERIC_ALL) ? 0 : hd;
+    const int nx = x - 2 * o, ny = y - 2 * o;
+    const int cpt = (kind == SUM_GENERIC || kind == SUM_GENERIC_ALL) ? 1 : 2, tile_cols = 128 * cpt;
     const int rows = gpu_tile_rows(kind, nx, ny);
     const int gx = (nx + tile_cols - 1) / tile_cols, gy = (ny + rows - 1) / rows;
     const long ntiles = (long)gx * gy;
@@ -120,14 +125,14 @@ static double gpu_order_sum(const double* val, int x, int y, int hd, int kind)
 #pragma omp parallel for schedule(static)
     for (long tile = 0; tile < ntiles; ++tile) {
         const int bx = (int)(tile % gx), by = (int)(tile / gx);
-        const int j0 = hd + by * rows, j1 = (j0 + rows < y - hd) ? j0 + rows : y - hd;
+        const int j0 = o + by * rows, j1 = (j0 + rows < y - o) ? j0 + rows : y - o;
         double t[128];
         for (int tx = 0; tx < 128; ++tx) {
             double acc = 0.0;
-            const int kk = hd + cpt * (bx * 128 + tx);
+            const int kk = o + cpt * (bx * 128 + tx);
             for (int jj = j0; jj < j1; ++jj)
                 for (int c = 0; c < cpt; ++c)
-                    if (kk + c < x - hd) acc += val[(long)(kk + c) + (long)jj * x];
+                    if (kk + c < x - o) acc += val[(long)(kk + c) + (long)jj * x];
             t[tx] = acc;
         }
         part[tile] = block128(t);
@@ -259,13 +264,13 @@ void orc_field_summary(int x, int y, int hd, const double* volume, const double*
                        double* vol, double* mass, double* ie, double* temp)
 {
     double r;
-    ND64_REDUCE(r, volume[index]);
+    ND64_REDUCE_K(r, volume[index], SUM_HOT_UR);
     *vol = r;
-    ND64_REDUCE(r, volume[index] * density[index]);
+    ND64_REDUCE_K(r, volume[index] * density[index], SUM_HOT_UR);
     *mass = r;
-    ND64_REDUCE(r, (volume[index] * density[index]) * energy0[index]);
+    ND64_REDUCE_K(r, (volume[index] * density[index]) * energy0[index], SUM_HOT_UR);
     *ie = r;
-    ND64_REDUCE(r, (volume[index] * density[index]) * u[index]);
+    ND64_REDUCE_K(r, (volume[index] * density[index]) * u[index], SUM_HOT_UR);
     *temp = r;
 }
 
@@ -358,7 +363,7 @@ void orc_cg_init(int x, int y, int hd, int coefficient, double rx, double ry,
         }
     }
     double s;
-    ND64_REDUCE(s, r[index] * p[index]);
+    ND64_REDUCE_K(s, r[index] * p[index], SUM_GENERIC_ALL);
     *rro += s;
 }
 
@@ -522,11 +527,17 @@ void orc_calculate_residual(int x, int y, int hd, const double* u, const double*
 }
 
 /* solver_methods.cpp:68-117; *norm ASSIGNED (:116) */
-void orc_calculate_2norm(int x, int y, int hd, const double* buffer, double* norm)
+/* kind: tile geometry of the GPU kernel that computes this sum (only the replay mode looks at it) */
+static void calculate_2norm_k(int x, int y, int hd, const double* buffer, double* norm, int kind)
 {
     double s;
-    ND64_REDUCE(s, buffer[index] * buffer[index]);
+    if (kind == SUM_HOT_FS) ND64_REDUCE_K(s, buffer[index] * buffer[index], SUM_HOT_FS);
+    else ND64_REDUCE_K(s, buffer[index] * buffer[index], SUM_HOT_UR);
     *norm = s;
+}
+void orc_calculate_2norm(int x, int y, int hd, const double* buffer, double* norm)
+{
+    calculate_2norm_k(x, y, hd, buffer, norm, SUM_HOT_UR);
 }
 
 /* solver_methods.cpp:120-145 */
@@ -852,10 +863,12 @@ static int cg_driver(run_t* R, double rx, double ry, double* error)
     return tt;
 }
 
-static double norm2_all(run_t* R, int which /*0=r,1=u0*/)
+/* folded: the GPU backend computes this norm inside the one-pass Chebyshev / PPCG kernel that produces r (tall
+ * stencil tiles), not with the calculate_2norm kernel: same values, another summation tree in the replay mode. */
+static double norm2_all(run_t* R, int which /*0=r,1=u0*/, int folded)
 {
     double loc[64];
-    FOR_CHUNKS orc_calculate_2norm(K->x, K->y, R->hd, which ? K->u0 : K->r, &loc[c]);
+    FOR_CHUNKS calculate_2norm_k(K->x, K->y, R->hd, which ? K->u0 : K->r, &loc[c], folded ? SUM_HOT_FS : SUM_HOT_UR);
     return sum_ranks(loc, R->nc);
 }
 
@@ -900,7 +913,7 @@ static int cheby_driver(run_t* R, double rx, double ry, double* error, int* n_ch
             FOR_CHUNKS orc_cheby_iterate(K->x, K->y, R->hd, R->cheby_alphas[num_cheby_iters],
                                          R->cheby_betas[num_cheby_iters], K->u, K->u0, K->kx, K->ky,
                                          K->p, K->r, K->w);
-            if (calc_2norm) *error = norm2_all(R, 0);
+            if (calc_2norm) *error = norm2_all(R, 0, 1);
             if (num_cheby_iters == 1)
                 est_iterations = orc_cheby_est_iterations(R->eigmin, R->eigmax, *error, bb);
         }
@@ -956,7 +969,7 @@ static int ppcg_driver(run_t* R, double rx, double ry, double* error, int* n_ppc
             }
             reset_fields(R);
             R->fields[ORC_F_P] = 1;
-            double rrn = norm2_all(R, 0);
+            double rrn = norm2_all(R, 0, 1);
             double beta = rrn / rro;
             FOR_CHUNKS orc_cg_calc_p(K->x, K->y, R->hd, beta, K->r, K->p);
             *error = rrn;
@@ -1118,7 +1131,7 @@ int orc_run_deck(const orc_deck* d, orc_result* res, double* u_out, double* ener
         res->eigmax[step] = R->eigmax;
         /* solve_finished_driver.c:7-43 (check_result defaults to 1; the norm is unused) */
         FOR_CHUNKS orc_calculate_residual(K->x, K->y, hd, K->u, K->u0, K->kx, K->ky, K->r);
-        (void)norm2_all(R, 0);
+        (void)norm2_all(R, 0, 0);
         FOR_CHUNKS orc_finalise(K->x, K->y, hd, K->u, K->density, K->energy);
         R->fields[ORC_F_ENERGY1] = 1;
         halo_update(R, 1);

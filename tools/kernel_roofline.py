@@ -22,7 +22,7 @@ app.solve(0)
 K = [(0, "cg_calc_w", 32), (1, "cg_calc_ur", 48), (2, "cg_calc_p", 24), (4, "cheby_iterate", 64),
      (5, "cheby_calc_u", 24), (15, "cheby_init", 56), (6, "ppcg_calc_ur", 56), (7, "ppcg_calc_sd", 24),
      (8, "jacobi_iterate(+copy)", 56), (9, "calculate_residual", 40), (10, "calculate_2norm", 8),
-     (11, "field_summary", 32), (12, "cg_init (3 kernels)", 120), (13, "finalise", 24), (14, "copy_u", 16),
+     (11, "field_summary", 32), (12, "cg_init (one pass; 120 B algorithmic, 64 moved)", 120), (13, "finalise", 24), (14, "copy_u", 16),
      (16, "cheby fused iter+calc_u", 64), (17, "ppcg fused ur+sd", 64), (3, "cg_calc_pw (fused)", 48)]
 print("# %dx%d mesh, peak = %.0f GB/s (MEASURED_PEAKS.json)" % (n, n, peak))
 print("%-24s %8s %10s %9s %6s" % ("kernel", "B/cell", "ms/launch", "GB/s", "frac"))
