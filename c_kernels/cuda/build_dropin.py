@@ -1,7 +1,7 @@
 """Compiles the UNMODIFIED reference host (where it lies under /root/reference) against this backend
-directory, exactly as `make KERNELS=cuda` would, into oracle/_ref/ (git-ignored; travels to the GPU box):
-    oracle/_ref/tealeaf_cuda            host-driven plugin path (drivers/*.c call run_* per kernel)
-    oracle/_ref/tealeaf_cuda_resident   -DDIFFUSE_OVERLOAD: device-resident solver loop
+directory, exactly as `make KERNELS=cuda` would, into c_kernels/cuda/bin/ (git-ignored; travels to the GPU box):
+    c_kernels/cuda/bin/tealeaf_cuda            host-driven plugin path (drivers/*.c call run_* per kernel)
+    c_kernels/cuda/bin/tealeaf_cuda_resident   -DDIFFUSE_OVERLOAD: device-resident solver loop
 Does nothing when /root/reference is absent (the GPU box uses the prebuilt files)."""
 import glob
 import os
@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get("TL_REFERENCE", "/root/reference/TeaLeaf")
-OUT = os.path.join(ROOT, "oracle", "_ref")
+OUT = os.path.join(HERE, "bin")
 CXX = "/usr/bin/g++"
 
 
@@ -41,7 +41,7 @@ def build():
                 raise RuntimeError("drop-in compile failed")
         exe = os.path.join(OUT, name)
         subprocess.check_call([CXX, "-o", exe] + objs + ["-L" + libdir, "-ltealeaf_b200",
-                                                          "-Wl,-rpath,$ORIGIN/../../exploringsycl_b200", "-lm", "-lrt"])
+                                                          "-Wl,-rpath,$ORIGIN/../../../exploringsycl_b200", "-lm", "-lrt"])
 
 
 if __name__ == "__main__":

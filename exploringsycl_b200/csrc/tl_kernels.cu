@@ -669,39 +669,62 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
         if (conv) return;
     }
     const HotTile t = hot_tile(g, rows, rev);
+    const int lane = threadIdx.x & 31;
+    // Left / right neighbours of the thread's two cells come from the adjacent lanes by shuffle; only the two edge lanes
+    // of a warp (and the lane next to the row end) load theirs -- in the row's load phase, with everything else.
+    const bool load_l = t.v0 && lane == 0;
+    const bool load_r = t.v1 && (lane == 31 || t.kk + 2 > g.x - g.hd - 1);
+    auto sides = [&](double2 c, double el, double er, double& l, double& rr) { // all lanes of the warp
+        const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);
+        const double sr = __shfl_down_sync(0xffffffffu, c.x, 1);
+        l = load_l ? el : sl;
+        rr = load_r ? er : sr;
+    };
     double acc[1] = {0.0};
-    if (t.v0) {
+    {
         long i = t.i;
         const long pitch = g.pitch;
-        double2 pm = ldp2<true>(p + i - pitch);
-        double2 pc = ldp2<true>(p + i);
-        double pl = ldp1<true>(p + i - 1), pr = ldp1<true>(p + i + 2);
-        double2 kyc = ld2_ro(ky + i);
+        double2 pm = make_double2(0.0, 0.0), pc = pm, kyc = pm;
+        double pl, pr, el = 0.0, er = 0.0;
+        if (t.v0) {
+            pm = ldp2<true>(p + i - pitch);
+            pc = ldp2<true>(p + i);
+            if (load_l) el = ldp1<true>(p + i - 1);
+            if (load_r) er = ldp1<true>(p + i + 2);
+            kyc = ld2_ro(ky + i);
+        }
+        sides(pc, el, er, pl, pr);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             double2 pn[U], kyn[U], kxc[U];
-            double kxr[U], pln[U], prn[U];
+            double kxr[U], eln[U], ern[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (jb + u < t.j1) {
+                pn[u] = make_double2(0.0, 0.0);
+                eln[u] = ern[u] = 0.0;
+                if (t.v0 && jb + u < t.j1) {
                     const long iu = i + u * pitch;
                     pn[u] = ldp2<true>(p + iu + pitch);
                     kyn[u] = ld2_ro(ky + iu + pitch);
                     kxc[u] = ld2_ro(kx + iu);
                     kxr[u] = __ldg(kx + iu + 2);
-                    pln[u] = ldp1<true>(p + iu + pitch - 1);
-                    prn[u] = ldp1<true>(p + iu + pitch + 2);
+                    if (load_l) eln[u] = ldp1<true>(p + iu + pitch - 1);
+                    if (load_r) ern[u] = ldp1<true>(p + iu + pitch + 2);
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (jb + u < t.j1) {
-                    double2 wv;
-                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pc.y, pm.x, pn[u].x);
-                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
-                    st_pair(w + i + u * pitch, wv, t.v1);
-                    acc[0] += wv.x * pc.x;
-                    if (t.v1) acc[0] += wv.y * pc.y;
-                    pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln[u]; pr = prn[u];
+                if (jb + u < t.j1) { // warp-uniform
+                    double pln, prn;
+                    sides(pn[u], eln[u], ern[u], pln, prn);
+                    if (t.v0) {
+                        double2 wv;
+                        wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pc.y, pm.x, pn[u].x);
+                        wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
+                        st_pair(w + i + u * pitch, wv, t.v1);
+                        acc[0] += wv.x * pc.x;
+                        if (t.v1) acc[0] += wv.y * pc.y;
+                        pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln; pr = prn;
+                    }
                 }
             }
         }
@@ -1075,45 +1098,70 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
     // iteration's old p there, so they are written to p_out's halo
     const bool halo_l = MULTI && t.v0 && !(ext_mask & 1) && t.kk == klo;
     const bool halo_r = MULTI && !(ext_mask & 2) && ((t.v1 && t.kk + 1 == khi) || (t.v0 && !t.v1 && t.kk == khi));
-    auto pnew2 = [&](long i) {
-        double2 a = ldp2<true>(p_in + i);
-        const double2 b = ldp2<true>(r + i);
-        a.x = beta * a.x + b.x;
-        a.y = beta * a.y + b.y;
-        return a;
+    // Raw (p, r) pairs: every global load of a row is issued in the row's LOAD phase -- also the two scalar pairs the
+    // edge lanes of a warp need for their outer neighbours -- and combined (beta p + r) in the compute phase.  (When the
+    // scalar loads sat behind the shuffles the compiler scheduled them after the row's vector loads had returned:
+    // two dependent memory latencies per row, +20 % on the multi-rank instantiation.)
+    struct Raw2 { double2 p, r; };
+    struct Side { double pl, rl, pr, rr; };
+    auto load2 = [&](long i) { return Raw2{ldp2<true>(p_in + i), ldp2<true>(r + i)}; };
+    auto comb2 = [&](const Raw2& q) { return make_double2(beta * q.p.x + q.r.x, beta * q.p.y + q.r.y); };
+    auto load_sides = [&](long i) {
+        Side q = {0.0, 0.0, 0.0, 0.0};
+        if (load_l) {
+            q.pl = ldp1<true>(p_in + i - 1);
+            q.rl = ldp1<true>(r + i - 1);
+        }
+        if (load_r) {
+            q.pr = ldp1<true>(p_in + i + 2);
+            q.rr = ldp1<true>(r + i + 2);
+        }
+        return q;
     };
-    auto pnew1 = [&](long i) { return beta * ldp1<true>(p_in + i) + ldp1<true>(r + i); };
-    // sides of an updated row held as double2 `c` in every lane
-    auto sides = [&](double2 c, long i, double& l, double& rr) {
+    // left / right neighbours of an updated row held as double2 `c` in every lane (called by all lanes of the warp)
+    auto sides = [&](double2 c, const Side& q, double& l, double& rr) {
         const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);
         const double sr = __shfl_down_sync(0xffffffffu, c.x, 1);
         l = mir_l ? c.x : sl;
-        if (load_l) l = pnew1(i - 1);
+        if (load_l) l = beta * q.pl + q.rl;
         rr = mir_r1 ? c.y : sr;
-        if (load_r) rr = pnew1(i + 2);
+        if (load_r) rr = beta * q.pr + q.rr;
     };
     double acc[1] = {0.0};
     long i = t.i;
     double2 pm = make_double2(0.0, 0.0), pc = pm, kyc = pm;
     double pl = 0.0, pr = 0.0;
-    if (t.v0) {
-        pc = pnew2(i);
+    {
         const bool mir_b = (ext_mask & 4) && t.j0 == jlo;
-        pm = mir_b ? pc : pnew2(i - pitch);
-        if (MULTI && !(ext_mask & 4) && t.j0 == jlo) st_pair(p_out + i - pitch, pm, t.v1); // bottom halo row
-        kyc = ld2_ro(ky + i);
+        Raw2 rc = {pm, pm}, rm = {pm, pm};
+        Side sc = {0.0, 0.0, 0.0, 0.0};
+        if (t.v0) {
+            rc = load2(i);
+            if (!mir_b) rm = load2(i - pitch);
+            sc = load_sides(i);
+            kyc = ld2_ro(ky + i);
+        }
+        pc = comb2(rc);
+        pm = mir_b ? pc : comb2(rm);
+        if (MULTI && t.v0 && !(ext_mask & 4) && t.j0 == jlo) st_pair(p_out + i - pitch, pm, t.v1); // bottom halo row
+        sides(pc, sc, pl, pr);
     }
-    sides(pc, i, pl, pr);
     for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
-        double2 pn[U], kyn[U], kxc[U];
+        Raw2 rn[U];
+        Side sn[U];
+        double2 kyn[U], kxc[U];
         double kxr[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            pn[u] = make_double2(0.0, 0.0);
+            rn[u].p = rn[u].r = make_double2(0.0, 0.0);
+            sn[u] = Side{0.0, 0.0, 0.0, 0.0};
             if (t.v0 && jb + u < t.j1) {
                 const long iu = i + u * pitch;
                 const bool mir_t = (ext_mask & 8) && (jb + u == jhi);
-                if (!mir_t) pn[u] = pnew2(iu + pitch);
+                if (!mir_t) {
+                    rn[u] = load2(iu + pitch);
+                    sn[u] = load_sides(iu + pitch);
+                }
                 kyn[u] = ld2_ro(ky + iu + pitch);
                 kxc[u] = ld2_ro(kx + iu);
                 kxr[u] = __ldg(kx + iu + 2);
@@ -1124,14 +1172,14 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
             if (jb + u < t.j1) { // warp-uniform
                 const long iu = i + u * pitch;
                 const bool mir_t = (ext_mask & 8) && (jb + u == jhi);
-                if (mir_t) pn[u] = pc;
+                const double2 pn = mir_t ? pc : comb2(rn[u]);
                 double pln, prn;
-                sides(pn[u], iu + pitch, pln, prn);
+                sides(pn, sn[u], pln, prn); // (the mirrored top row's sides are never used: it is the tile's last row)
                 if (t.v0) {
                     double2 wv;
                     const double pr0 = mir_r0 ? pc.x : pc.y; // right neighbour of cell 0
-                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pr0, pm.x, pn[u].x);
-                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
+                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pr0, pm.x, pn.x);
+                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn.y);
                     st_pair(w + iu, wv, t.v1);
                     st_pair(p_out + iu, pc, t.v1);
                     if constexpr (MULTI) {
@@ -1140,11 +1188,11 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
                             if (t.v1) p_out[iu + 2] = pr;
                             else p_out[iu + 1] = pc.y;
                         }
-                        if (!(ext_mask & 8) && jb + u == jhi) st_pair(p_out + iu + pitch, pn[u], t.v1); // top halo row
+                        if (!(ext_mask & 8) && jb + u == jhi) st_pair(p_out + iu + pitch, pn, t.v1); // top halo row
                     }
                     acc[0] += wv.x * pc.x;
                     if (t.v1) acc[0] += wv.y * pc.y;
-                    pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln; pr = prn;
+                    pm = pc; pc = pn; kyc = kyn[u]; pl = pln; pr = prn;
                 }
             }
         }

@@ -1,5 +1,5 @@
 """Drop-in proof: the UNMODIFIED reference host (main.c / diffuse.c / drivers/*.c compiled from
-/root/reference by c_kernels/cuda/build_dropin.py into oracle/_ref/) drives this backend through the
+/root/reference by c_kernels/cuda/build_dropin.py into c_kernels/cuda/bin/) drives this backend through the
 reference's own kernel_interface.h symbols.  Its printed iteration counts and final temperature must
 match the oracle.  Skipped where the prebuilt binaries are absent."""
 import os
@@ -13,7 +13,7 @@ from oracle import oracle as O
 from tl_testutil import DECKS, GOLDEN, ROOT, rel
 
 pytestmark = pytest.mark.gpu
-BIN = {k: os.path.join(ROOT, "oracle", "_ref", k) for k in ("tealeaf_cuda", "tealeaf_cuda_resident")}
+BIN = {k: os.path.join(ROOT, "c_kernels", "cuda", "bin", k) for k in ("tealeaf_cuda", "tealeaf_cuda_resident")}
 
 
 def run_bin(name, deck, tmp_path):
@@ -68,3 +68,30 @@ def test_jacobi_deck(binary, tmp_path):
     r = O.run_deck(O.make_deck(10, solver=O.JACOBI))
     assert it == r["iters_a"]
     assert rel(actual, r["temp"]) < 1e-10
+
+
+def test_resident_binary_reports_all_four_sums_and_a_json_sidecar(tmp_path):
+    """the reference computes vol / mass / ie / temp (field_summary_driver.c:11-30) and prints only
+    temp; the DIFFUSE_OVERLOAD binary adds a 'Field summary:' line, a 'Solver rate:' line per step and tea.json --
+    the reference's own lines stay."""
+    import json
+    out = run_bin("tealeaf_cuda_resident", "tea_250_cg.in", tmp_path)
+    assert "PASSED" in out and out.count("Solver rate:") == 10
+    r = O.run_deck(O.make_deck(250))
+    m = re.findall(r"Field summary:\s+vol (\S+) mass (\S+) ie (\S+) temp (\S+)", out)
+    assert len(m) == 2  # step 1 (summary_frequency 10) and the final one
+    for got, key in zip(m[-1], ("vol", "mass", "ie", "temp")):
+        assert rel(float(got), r[key]) < 1e-10, key
+    side = json.load(open(tmp_path / "tea.json"))
+    assert side["solver"] == "cg" and side["grid"] == [250, 250] and len(side["steps"]) == 10
+    assert [s["iters_a"] for s in side["steps"]] == [int(v) for v in re.findall(r"(?m)^CG:\s+(\d+) iterations", out)]
+    assert all(s["cell_iters_per_s"] > 0 and s["algorithmic_gb_per_s"] > 0 for s in side["steps"])
+    for key, name in (("vol", "volume"), ("mass", "mass"), ("ie", "internal_energy"), ("temp", "temperature")):
+        assert rel(side["field_summary"][name], r[key]) < 1e-10
+    # TL_REPORT=0: nothing but the reference's lines
+    os.environ["TL_REPORT"] = "0"
+    try:
+        quiet = run_bin("tealeaf_cuda_resident", "tea_10_cg.in", tmp_path)
+    finally:
+        del os.environ["TL_REPORT"]
+    assert "Field summary:" not in quiet and "Solver rate:" not in quiet and "PASSED" in quiet

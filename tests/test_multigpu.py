@@ -208,7 +208,7 @@ def test_reference_host_on_two_ranks(binary, tmp_path):
     from tl_testutil import GOLDEN, ROOT
     if ngpus() < 2:
         pytest.skip("needs 2 GPUs")
-    exe = os.path.join(ROOT, "oracle", "_ref", binary)
+    exe = os.path.join(ROOT, "c_kernels", "cuda", "bin", binary)
     if not os.path.exists(exe):
         pytest.skip("%s not built" % binary)
     shutil.copy(os.path.join(DECKS, "tea_250_cg.in"), tmp_path / "tea.in")
