@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other named configs at N > 1")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="skip the stamped solve behind iteration_profile")
     ap.add_argument("--mesh", type=int, nargs=2, default=None)
     ap.add_argument("--solver", default="cg", choices=["cg", "cheby", "ppcg", "jacobi"],
                     help="non-default solvers are reported under their own metric name (BASELINE configs[3])")
@@ -213,6 +214,9 @@ def main():
         t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def min_over_ranks(v):
+        return -max_over_ranks(-v)
 
     def sum_over_ranks(v):
         if world == 1:
@@ -280,6 +284,19 @@ def main():
     fuse_env = int(os.environ["TL_BENCH_FUSED"]) if os.environ.get("TL_BENCH_FUSED") is not None else None
     cells = nx * ny
 
+    # ---------------- loop form: two kernels (fused p-update + matvec) or three, whichever is faster here ----------------
+    # Both forms give bit-identical results (parity leg above).  With left/right neighbours the better one depends on the
+    # chunk shape, so at N >= 4 both are timed on a capped solve BEFORE the timed region and the faster one is used;
+    # every rank takes the decision from the same max-over-ranks times.
+    loop_tune = None
+    if world >= 4 and fuse_env is None and args.solver == "cg":
+        t3 = timed_case(nx, ny, "cg", 300, 1, 1, 0)
+        t2 = timed_case(nx, ny, "cg", 300, 1, 1, 2)
+        fuse_env = 2 if t2["gpu_s"] <= t3["gpu_s"] else 0
+        loop_tune = {"three_kernel_ms_per_iter": 1e3 * t3["gpu_s"] / max(t3["iters"], 1),
+                     "fused_ms_per_iter": 1e3 * t2["gpu_s"] / max(t2["iters"], 1),
+                     "chosen": "fused" if fuse_env == 2 else "three_kernel"}
+
     # ---------------- value: state resident in HBM ----------------
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -291,6 +308,11 @@ def main():
     ch = app.chunk
     value, gpu_s, launches = main_case["value"], main_case["gpu_s"], main_case["launches"]
     inner = s.ppcg_inner_steps if args.solver == "ppcg" else 0
+
+    # ---------------- where an iteration's time goes: %globaltimer stamps of the loop kernels (all ranks) ----------------
+    iteration_profile = None
+    if args.solver == "cg" and not args.no_profile:
+        iteration_profile = stamp_profile(L, app, s, world, max_over_ranks, min_over_ranks)
 
     # ---------------- e2e: host buffers, copies inside the timed region ----------------
     e2e = None
@@ -408,7 +430,8 @@ def main():
                            if fused_run
                            else "cg_calc_w + cg_calc_ur + cg_calc_p (104 B/cell moved)"},
                 "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "parity": parity, "extra": extra, "wall_s": wall,
+                "cpu_baseline": cpu, "parity": parity, "iteration_profile": iteration_profile, "loop_form_tuning": loop_tune,
+                "extra": extra, "wall_s": wall,
                 "summary": main_case["summary"]}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -417,6 +440,59 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def stamp_profile(L, app, s, world, max_over_ranks, min_over_ranks, iters=300):
+    """One more solve of the benchmark problem, capped at `iters` iterations, with the loop kernels' %globaltimer stamps
+    switched on (tl_stamps_enable, see tools/stamps.py).  Medians over the iterations, in microseconds; for N > 1 the
+    minimum and maximum over the ranks (clocks are per GPU: only same-rank differences are taken).
+      body   first CTA past its dependency wait -> tail CTA holds this rank's partial sum (streaming + grid reduction)
+      gather tail CTA: NVLink all-gather of the ranks' partials (latency on the last rank to arrive, + skew on the others)
+      halo   tail CTA: halo hand-shake with the neighbours
+      gap    end of the kernel's tail -> first CTA of the next kernel past its wait"""
+    import numpy as np
+    from exploringsycl_b200._lib import check
+    ch = app.chunk
+    keep = s.max_iters
+    s.max_iters = iters
+    check(L.tl_stamps_enable(ch.handle, iters))
+    info = app.solve(0)
+    n = info.total_iters
+    buf = (C.c_ulonglong * (n * 12))()
+    check(L.tl_stamps_read(ch.handle, buf, n))
+    check(L.tl_stamps_enable(ch.handle, 0))
+    s.max_iters = keep
+    t = np.ctypeslib.as_array(buf).reshape(n, 3, 4).astype(np.int64)
+    fused = bool(L.tl_cg_loop_is_fused(ch.handle, s.fuse_p_into_w))
+    kernels = [0, 1] if fused else [0, 1, 2]
+    names = {0: "cg_calc_pw" if fused else "cg_calc_w", 1: "cg_calc_ur", 2: "cg_calc_p"}
+    sl = slice(5, n - 1)
+
+    def med(x):
+        return float(np.median(x[sl])) / 1e3 if n > 8 else 0.0
+
+    out = {"iterations": n, "loop": "fused" if fused else "three_kernel", "unit": "us (median over iterations)"}
+    last = {}
+    vals = {}
+    for kq in kernels:
+        t0, t1, t2, t3 = (t[:, kq, j] for j in range(4))
+        if kq == 2:
+            last[kq] = np.maximum(t0, t3)
+            vals[names[kq] + ".body_incl_handshake"] = med(t3 - t0) if t3.any() else 0.0
+            continue
+        last[kq] = np.maximum(np.maximum(t1, t2), t3)
+        vals[names[kq] + ".body"] = med(t1 - t0)
+        vals[names[kq] + ".gather"] = med(t2 - t1)
+        if t3.any():
+            vals[names[kq] + ".halo"] = med(t3 - t1)
+    for i_, kq in enumerate(kernels):
+        nxt = kernels[(i_ + 1) % len(kernels)]
+        nt0 = t[:, nxt, 0] if nxt != kernels[0] else np.roll(t[:, nxt, 0], -1)
+        vals[names[kq] + ".gap_to_next"] = med(nt0 - last[kq])
+    vals["iteration"] = med(np.roll(t[:, 0, 0], -1) - t[:, 0, 0])
+    for k_, v in vals.items():  # same keys in the same order on every rank
+        out[k_] = v if world == 1 else {"min": min_over_ranks(v), "max": max_over_ranks(v)}
+    return out
 
 
 def parity_leg(L, new_comms, world, rank, local_rank, sum_over_ranks):

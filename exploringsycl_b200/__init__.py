@@ -5,5 +5,5 @@ Only what the hot path needs lives here: csrc/ (CUDA kernels + the C-ABI of incl
 and tealeaf.py (the host-side mirror of the reference interface). No CPU fallback exists.
 """
 from ._lib import TeaLeafError, lib, LIB_PATH  # noqa: F401
-from .tealeaf import (Chunk, Comms, Settings, State, TeaLeaf, read_config, decompose_field,  # noqa: F401
-                      get_checking_value)
+from .tealeaf import (Chunk, Comms, Settings, State, TeaLeaf, read_config, read_config_clean,  # noqa: F401
+                      settings_overload, write_to_visit, decompose_field, get_checking_value)

@@ -652,7 +652,7 @@ int tlk_hot_check(const tl_chunk* c, dim3 grid)
 // 32 B/cell of HBM traffic: read p, kx, ky; write w.  Rows j-1, j, j+1 of p and rows j, j+1 of ky
 // slide through registers, so every element is requested from L2 once per tile.
 template <int U, bool MULTI>
-__global__ void __launch_bounds__(TL_TPB, 8)
+__global__ void __launch_bounds__(TL_TPB)
 k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double* __restrict__ ky,
             double* __restrict__ w, double* __restrict__ d_alphas, RedArgs ra, int mode, int rows, int rev,
             const MultiCtx mc)
@@ -669,62 +669,43 @@ k_cg_calc_w(Geo g, const double* p, const double* __restrict__ kx, const double*
         if (conv) return;
     }
     const HotTile t = hot_tile(g, rows, rev);
-    const int lane = threadIdx.x & 31;
-    // Left / right neighbours of the thread's two cells come from the adjacent lanes by shuffle; only the two edge lanes
-    // of a warp (and the lane next to the row end) load theirs -- in the row's load phase, with everything else.
-    const bool load_l = t.v0 && lane == 0;
-    const bool load_r = t.v1 && (lane == 31 || t.kk + 2 > g.x - g.hd - 1);
-    auto sides = [&](double2 c, double el, double er, double& l, double& rr) { // all lanes of the warp
-        const double sl = __shfl_up_sync(0xffffffffu, c.y, 1);
-        const double sr = __shfl_down_sync(0xffffffffu, c.x, 1);
-        l = load_l ? el : sl;
-        rr = load_r ? er : sr;
-    };
     double acc[1] = {0.0};
-    {
+    if (t.v0) {
+        // p is complete when this kernel's dependency wait returns and nobody writes it while the kernel runs (several
+        // ranks: the neighbours' halo stores belong to calc_p, whose tail CTA hand-shook before it completed), so the
+        // default L1-allocating loads are legal here: the left / right neighbours are scalar L1 hits of lines the
+        // adjacent lanes' vector loads bring in.
         long i = t.i;
         const long pitch = g.pitch;
-        double2 pm = make_double2(0.0, 0.0), pc = pm, kyc = pm;
-        double pl, pr, el = 0.0, er = 0.0;
-        if (t.v0) {
-            pm = ldp2<true>(p + i - pitch);
-            pc = ldp2<true>(p + i);
-            if (load_l) el = ldp1<true>(p + i - 1);
-            if (load_r) er = ldp1<true>(p + i + 2);
-            kyc = ld2_ro(ky + i);
-        }
-        sides(pc, el, er, pl, pr);
+        double2 pm = ld2(p + i - pitch);
+        double2 pc = ld2(p + i);
+        double pl = p[i - 1], pr = p[i + 2];
+        double2 kyc = ld2_ro(ky + i);
         for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
             double2 pn[U], kyn[U], kxc[U];
-            double kxr[U], eln[U], ern[U];
+            double kxr[U], pln[U], prn[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                pn[u] = make_double2(0.0, 0.0);
-                eln[u] = ern[u] = 0.0;
-                if (t.v0 && jb + u < t.j1) {
+                if (jb + u < t.j1) {
                     const long iu = i + u * pitch;
-                    pn[u] = ldp2<true>(p + iu + pitch);
+                    pn[u] = ld2(p + iu + pitch);
                     kyn[u] = ld2_ro(ky + iu + pitch);
                     kxc[u] = ld2_ro(kx + iu);
                     kxr[u] = __ldg(kx + iu + 2);
-                    if (load_l) eln[u] = ldp1<true>(p + iu + pitch - 1);
-                    if (load_r) ern[u] = ldp1<true>(p + iu + pitch + 2);
+                    pln[u] = p[iu + pitch - 1];
+                    prn[u] = p[iu + pitch + 2];
                 }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (jb + u < t.j1) { // warp-uniform
-                    double pln, prn;
-                    sides(pn[u], eln[u], ern[u], pln, prn);
-                    if (t.v0) {
-                        double2 wv;
-                        wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pc.y, pm.x, pn[u].x);
-                        wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
-                        st_pair(w + i + u * pitch, wv, t.v1);
-                        acc[0] += wv.x * pc.x;
-                        if (t.v1) acc[0] += wv.y * pc.y;
-                        pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln; pr = prn;
-                    }
+                if (jb + u < t.j1) {
+                    double2 wv;
+                    wv.x = smvp(kxc[u].x, kxc[u].y, kyc.x, kyn[u].x, pc.x, pl, pc.y, pm.x, pn[u].x);
+                    wv.y = smvp(kxc[u].y, kxr[u], kyc.y, kyn[u].y, pc.y, pc.x, pr, pm.y, pn[u].y);
+                    st_pair(w + i + u * pitch, wv, t.v1);
+                    acc[0] += wv.x * pc.x;
+                    if (t.v1) acc[0] += wv.y * pc.y;
+                    pm = pc; pc = pn[u]; kyc = kyn[u]; pl = pln[u]; pr = prn[u];
                 }
             }
         }
@@ -1146,6 +1127,7 @@ k_cg_calc_pw(Geo g, const double* p_in, double* __restrict__ p_out, const double
         if (MULTI && t.v0 && !(ext_mask & 4) && t.j0 == jlo) st_pair(p_out + i - pitch, pm, t.v1); // bottom halo row
         sides(pc, sc, pl, pr);
     }
+#pragma unroll 1
     for (int jb = t.j0; jb < t.j1; jb += U, i += U * pitch) {
         Raw2 rn[U];
         Side sn[U];

@@ -76,6 +76,8 @@ class Settings:  # settings.h:64-123 with the defaults of settings.h:15-45
     dy: float = 0.0
     fields_to_exchange: List[bool] = dc_field(default_factory=lambda: [False] * NUM_FIELDS)
     # extensions of this backend (not in the reference)
+    profiler_on: bool = False   # deck key the reference ignores (read_config_clean)
+    deck_warnings: List[str] = dc_field(default_factory=list)
     batch: int = 0
     fuse_p_into_w: int = 1  # 0: reference kernel sequence; 1: auto; 2: always fused (bit-identical), see tl_solve_opts
 
@@ -123,9 +125,14 @@ def _atoi(tok):
     return int(m.group(0)) if m else 0
 
 
-def read_config(path, settings: Optional[Settings] = None):
+def read_config(path, settings: Optional[Settings] = None, hygiene: bool = False):
     """parse_config.c:14-74: returns (settings, states). States' extents are shrunk by dx/100
-    (parse_config.c:253-260)."""
+    (parse_config.c:253-260).
+
+    hygiene=False (default) reproduces the reference parser, quirks included (tests pin it against the reference's
+    own parse_config.c).  hygiene=True is the cleaned-up reader of SURVEY.md 8f-4, see read_config_clean()."""
+    if hygiene:
+        return read_config_clean(path, settings)
     s = settings or Settings()
     with open(path) as fh:
         lines = fh.readlines()
@@ -197,6 +204,161 @@ def read_config(path, settings: Optional[Settings] = None):
         st.defined = True
     s.num_states = num_states
     return s, states
+
+
+# keys of read_settings (parse_config.c:88-184): name -> (attribute, kind); upstream decks spell the solver keys with
+# a tl_ prefix (Benchmarks/tea_bm_1.out:24-26: tl_max_iters, tl_use_cg, tl_eps), which the reference silently ignores
+_CLEAN_KEYS = {
+    "initial_timestep": ("dt_init", float), "end_time": ("end_time", float), "end_step": ("end_step", int),
+    "xmin": ("grid_x_min", float), "ymin": ("grid_y_min", float), "xmax": ("grid_x_max", float),
+    "ymax": ("grid_y_max", float), "x_cells": ("grid_x_cells", int), "y_cells": ("grid_y_cells", int),
+    "summary_frequency": ("summary_frequency", int), "presteps": ("presteps", int),
+    "ppcg_inner_steps": ("ppcg_inner_steps", int), "epslim": ("eps_lim", float), "max_iters": ("max_iters", int),
+    "eps": ("eps", float), "num_chunks_per_rank": ("num_chunks_per_rank", int), "halo_depth": ("halo_depth", int),
+    "ch_cg_presteps": ("presteps", int), "ch_cg_epslim": ("eps_lim", float),
+}
+_CLEAN_SWITCHES = {
+    "check_result": ("check_result", True), "errswitch": ("error_switch", True),
+    "ch_cg_errswitch": ("error_switch", True), "preconditioner_on": ("preconditioner", True),
+    "use_jacobi": ("solver", JACOBI_SOLVER), "use_cg": ("solver", CG_SOLVER),
+    "use_chebyshev": ("solver", CHEBY_SOLVER), "use_ppcg": ("solver", PPCG_SOLVER),
+    "coefficient_density": ("coefficient", CONDUCTIVITY),
+    "coefficient_inverse_density": ("coefficient", RECIP_CONDUCTIVITY),
+    "profiler_on": ("profiler_on", True), "use_c_kernels": (None, None), "use_fortran_kernels": (None, None),
+}
+_CLEAN_IGNORED = ("test_problem", "visit_frequency", "tiles_per_task", "use_vector_loops", "reflective_boundary")
+
+
+def read_config_clean(path, settings: Optional[Settings] = None):
+    """The deck reader without the reference's parsing accidents.  Same keys and the same meaning on a
+    well-formed deck -- results are identical there -- but:
+      * keys are matched exactly, `key=value` or `key value`, so `eps` can no longer swallow an `epslim` line that comes
+        in the wrong order, and signed numbers keep their sign (read_value, parse_config.c:316-340, starts at the first
+        alphanumeric character: `xmin=-5.0` is read as 5.0 there);
+      * x_cells / y_cells are always honoured (the reference reads them only while the field still holds the default
+        10, parse_config.c:102-107: a way of letting -x / -y win that misfires for a deck value of 10);
+      * the tl_ spelling of upstream decks (tl_max_iters, tl_eps, tl_use_cg, tl_ppcg_inner_steps, tl_ch_cg_presteps,
+        ...) and `profiler_on` are understood instead of being dropped silently (parse_config.c:88-184);
+      * circular and point states need no xmax / ymax; unknown keys and malformed values are collected in
+        settings.deck_warnings instead of being ignored.
+    The dx/100 shrink of the state extents (parse_config.c:253-260) is semantics, not an accident: it is kept."""
+    s = settings or Settings()
+    preset_x, preset_y = s.grid_x_cells != 10, s.grid_y_cells != 10  # set by the caller (command line) before the deck
+    warnings = []
+    state_lines = []
+    with open(path) as fh:
+        lines = fh.readlines()
+    in_deck = not any(ln.strip().startswith("*tea") for ln in lines)
+    for raw in lines:
+        line = raw.split("!")[0].strip()
+        if line.startswith("*tea"):
+            in_deck = True
+            continue
+        if line.startswith("*endtea"):
+            break
+        if not in_deck or not line:
+            continue
+        tok = line.replace("=", " ").split()
+        key = tok[0][3:] if tok[0].startswith("tl_") else tok[0]
+        if key == "state":
+            state_lines.append(line)
+        elif key in _CLEAN_KEYS:
+            attr, kind = _CLEAN_KEYS[key]
+            try:
+                val = kind(float(tok[1])) if kind is int else float(tok[1])
+            except (IndexError, ValueError):
+                warnings.append("no numeric value for '%s': %r" % (tok[0], raw.rstrip()))
+                continue
+            if (attr == "grid_x_cells" and preset_x) or (attr == "grid_y_cells" and preset_y):
+                continue  # the command line wins
+            setattr(s, attr, val)
+        elif key in _CLEAN_SWITCHES:
+            attr, val = _CLEAN_SWITCHES[key]
+            if attr:
+                setattr(s, attr, val)
+        elif key not in _CLEAN_IGNORED:
+            warnings.append("unknown key '%s'" % tok[0])
+    if s.grid_x_cells <= 0 or s.grid_y_cells <= 0:
+        raise TeaLeafError("x_cells and y_cells must be positive (got %d x %d)" % (s.grid_x_cells, s.grid_y_cells))
+    s.dx = (s.grid_x_max - s.grid_x_min) / float(s.grid_x_cells)
+    s.dy = (s.grid_y_max - s.grid_y_min) / float(s.grid_y_cells)
+    parsed = {}
+    for line in state_lines:
+        tok = line.replace("=", " ").split()
+        try:
+            n = int(tok[1])
+            kv = dict(zip(tok[2::2], tok[3::2]))
+            st = State(defined=True, density=float(kv["density"]), energy=float(kv["energy"]))
+            if n > 1:
+                geom = kv.get("geometry", "rectangle")
+                st.geometry = {"rectangle": RECTANGULAR, "circular": CIRCULAR, "circle": CIRCULAR, "point": POINT}[geom]
+                st.x_min = float(kv["xmin"]) + s.dx / 100.0
+                st.y_min = float(kv["ymin"]) + s.dy / 100.0
+                if st.geometry == RECTANGULAR:
+                    st.x_max = float(kv["xmax"]) - s.dx / 100.0
+                    st.y_max = float(kv["ymax"]) - s.dy / 100.0
+                elif st.geometry == CIRCULAR:
+                    st.radius = float(kv["radius"])
+                    # what the reference holds after parsing xmax=0 / ymax=0 (never read for this geometry)
+                    st.x_max, st.y_max = float(kv.get("xmax", 0.0)) - s.dx / 100.0, float(kv.get("ymax", 0.0)) - s.dy / 100.0
+                else:
+                    st.x_max, st.y_max = float(kv.get("xmax", 0.0)) - s.dx / 100.0, float(kv.get("ymax", 0.0)) - s.dy / 100.0
+        except (KeyError, ValueError, IndexError) as e:
+            raise TeaLeafError("malformed state line %r (%s)" % (line, e))
+        if n in parsed:
+            raise TeaLeafError("State number %d defined twice." % n)
+        parsed[n] = st
+    if not parsed or sorted(parsed) != list(range(1, len(parsed) + 1)):
+        raise TeaLeafError("states must be numbered 1..N without gaps (got %s)" % sorted(parsed))
+    states = [parsed[n] for n in sorted(parsed)]
+    s.num_states = len(states)
+    s.deck_warnings = warnings
+    return s, states
+
+
+def settings_overload(settings: Settings, argv, hygiene: bool = False):
+    """main.c:61-99.  hygiene=False reproduces it: -solver / --solver / -s take the next word; -x and -y pass the OPTION
+    ITSELF to atoi (main.c:78,83), so `-x 4000` sets grid_x_cells to 0.  hygiene=True reads the number that follows."""
+    a = list(argv)
+    for n, w in enumerate(a):
+        if w in ("-solver", "--solver", "-s"):
+            if n + 1 == len(a):
+                break
+            names = {"cg": CG_SOLVER, "cheby": CHEBY_SOLVER, "ppcg": PPCG_SOLVER, "jacobi": JACOBI_SOLVER}
+            if a[n + 1] in names:
+                settings.solver = names[a[n + 1]]
+            elif hygiene:
+                raise TeaLeafError("unknown solver '%s' (cg, cheby, ppcg, jacobi)" % a[n + 1])
+        elif w in ("-x", "-y"):
+            if n + 1 == len(a):
+                break
+            if hygiene:
+                try:
+                    v = int(a[n + 1])
+                except ValueError:
+                    raise TeaLeafError("%s needs a cell count, got '%s'" % (w, a[n + 1]))
+                if v <= 0:
+                    raise TeaLeafError("%s needs a positive cell count" % w)
+            else:
+                v = _atoi(w)  # atoi("-x") == 0
+            setattr(settings, "grid_x_cells" if w == "-x" else "grid_y_cells", v)
+    return settings
+
+
+def write_to_visit(nx, ny, x_off, y_off, data, name, step, time, directory="."):
+    """shared.c:114-150 (write_to_visit, never called by the reference's own drivers): a brick-of-values header
+    <name><step>.bov + the raw little-endian doubles <name><step>.dat.  `data` is the nx x ny interior.  Unlike the
+    reference, BRICK_ORIGIN carries the chunk offset and VARIABLE the field name (it writes 0. 0. 0. and 'density')."""
+    data = np.ascontiguousarray(data, dtype="<f8")
+    assert data.shape == (ny, nx)
+    bov = os.path.join(directory, "%s%d.bov" % (name, step))
+    dat = "%s%d.dat" % (name, step)
+    with open(bov, "w") as f:
+        f.write("TIME: %.4f\nDATA_FILE: %s\nDATA_SIZE: %d %d 1\nDATA_FORMAT: DOUBLE\nVARIABLE: %s\n"
+                "DATA_ENDIAN: LITTLE\nCENTERING: zone\nBRICK_ORIGIN: %d. %d. 0.\nBRICK_SIZE: %d %d 1\n"
+                % (time, dat, nx, ny, name, x_off, y_off, nx, ny))
+    data.tofile(os.path.join(directory, dat))
+    return bov
 
 
 def get_checking_value(problems_path, settings):  # field_summary_driver.c:56-91

@@ -148,3 +148,86 @@ def test_decomposition_invariants_property():
         assert all(d["x_chunks"] * d["y_chunks"] == n for d in ds)
 
     check()
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY.md 8f-4: command-line and deck hygiene (opt-in; the default reader stays pinned to the reference's quirks)
+# ------------------------------------------------------------------------------------------------
+QUIRKY_DECK = """*tea
+state 1 density=100.0 energy=0.0001
+state 2 density=0.1 energy=25.0 geometry=circular xmin=-2.5 ymin=1.0 radius=3.0
+x_cells=10
+y_cells=40
+xmin=-5.0
+ymin=0.0
+xmax=5.0
+ymax=10.0
+initial_timestep=0.004
+end_step=3
+tl_max_iters=777
+tl_use_ppcg
+tl_ppcg_inner_steps=4
+eps 1.0e-12
+epslim 1.0e-3
+profiler_on
+frobnicate=1
+*endtea
+"""
+
+
+def test_clean_deck_reader_versus_reference_quirks(tmp_path):
+    from exploringsycl_b200 import Settings, TeaLeafError, read_config
+    from exploringsycl_b200.tealeaf import CIRCULAR, PPCG_SOLVER
+    deck = tmp_path / "tea.in"
+    deck.write_text(QUIRKY_DECK)
+    # the reference's reader (parse_config.c): sign dropped, tl_ keys and profiler_on ignored, circular state without
+    # xmax is an error ("Failed to find a value")
+    with pytest.raises(TeaLeafError):
+        read_config(str(deck))
+    deck.write_text(QUIRKY_DECK.replace("radius=3.0", "radius=3.0 xmax=0.0 ymax=0.0"))
+    q, _ = read_config(str(deck))
+    assert q.grid_x_min == 5.0 and q.max_iters == 10000 and q.solver == 1 and q.ppcg_inner_steps == 10
+    assert q.grid_x_cells == 10 and q.grid_y_cells == 40
+    # the clean reader
+    deck.write_text(QUIRKY_DECK)
+    s, states = read_config(str(deck), hygiene=True)
+    assert s.grid_x_min == -5.0 and s.grid_x_max == 5.0 and s.dx == 1.0
+    assert s.max_iters == 777 and s.solver == PPCG_SOLVER and s.ppcg_inner_steps == 4
+    assert s.eps == 1.0e-12 and s.eps_lim == 1.0e-3 and s.profiler_on
+    assert s.deck_warnings == ["unknown key 'frobnicate'"]
+    assert states[1].geometry == CIRCULAR and states[1].radius == 3.0
+    assert states[1].x_min == -2.5 + s.dx / 100.0 and states[1].y_min == 1.0 + s.dy / 100.0
+    # x_cells = 10 in the deck is honoured even though 10 is the default, and the command line wins over the deck
+    s2, _ = read_config(str(deck), Settings(grid_x_cells=64), hygiene=True)
+    assert s2.grid_x_cells == 64 and s2.grid_y_cells == 40
+    for bad in ("state 2 density=0.1", "x_cells=0"):
+        deck.write_text(QUIRKY_DECK.replace("x_cells=10", bad))
+        with pytest.raises(TeaLeafError):
+            read_config(str(deck), hygiene=True)
+
+
+def test_settings_overload_quirk_and_fix():
+    """main.c:76-85: `-x 4000` calls atoi("-x") -> 0 cells.  The hygienic overload reads the value."""
+    from exploringsycl_b200 import Settings, TeaLeafError, settings_overload
+    from exploringsycl_b200.tealeaf import CHEBY_SOLVER
+    s = settings_overload(Settings(), ["tealeaf", "-x", "4000", "-y", "2000", "-s", "cheby"])
+    assert (s.grid_x_cells, s.grid_y_cells, s.solver) == (0, 0, CHEBY_SOLVER)
+    s = settings_overload(Settings(), ["tealeaf", "-x", "4000", "-y", "2000", "--solver", "cheby"], hygiene=True)
+    assert (s.grid_x_cells, s.grid_y_cells, s.solver) == (4000, 2000, CHEBY_SOLVER)
+    with pytest.raises(TeaLeafError):
+        settings_overload(Settings(), ["tealeaf", "-x", "abc"], hygiene=True)
+    with pytest.raises(TeaLeafError):
+        settings_overload(Settings(), ["tealeaf", "-s", "multigrid"], hygiene=True)
+    assert settings_overload(Settings(), ["tealeaf", "-x"]).grid_x_cells == 10  # dangling option: ignored (main.c:77)
+
+
+def test_write_to_visit(tmp_path):
+    """shared.c:114-150: header lines and the raw doubles."""
+    import numpy as np
+    from exploringsycl_b200 import write_to_visit
+    data = np.arange(12.0).reshape(3, 4)
+    bov = write_to_visit(4, 3, 8, 16, data, "density", 7, 0.028, directory=str(tmp_path))
+    txt = open(bov).read().splitlines()
+    assert txt[0] == "TIME: 0.0280" and txt[1] == "DATA_FILE: density7.dat" and txt[2] == "DATA_SIZE: 4 3 1"
+    assert "DATA_FORMAT: DOUBLE" in txt and "CENTERING: zone" in txt and "BRICK_ORIGIN: 8. 16. 0." in txt
+    assert np.array_equal(np.fromfile(tmp_path / "density7.dat", dtype="<f8").reshape(3, 4), data)

@@ -132,7 +132,7 @@ def test_vectorised_streaming_kernels_on_odd_shapes(nx, ny, hd):
     assert np.array_equal(ch.read(2), en)
     err = ch.run_jacobi_iterate()
     u, r = f["u"].copy(), f["r"].copy()
-    oe = dbl(); L.orc_jacobi_iterate(x, y, hd, u, f["u0"], r, f["kx"], f["ky"], C.byref(oe))
+    oe = dbl(); L.orc_jacobi_iterate(x, y, hd, u, exp, r, f["kx"], f["ky"], C.byref(oe))  # u0 as copy_u left it
     assert np.array_equal(ch.read(3), u) and np.array_equal(ch.read(7), r)
     assert rel(err, oe.value) < 1e-13
     ch.close()
