@@ -614,14 +614,14 @@ static void tune_from_env()
     }
 }
 
-// Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read), but the tile count should sit
-// just under `ctas_per_sm` resident CTAs per SM so the whole grid is one balanced wave (profiles/tuning_r01.txt:
-// 4000x4000 at 8 CTAs per SM -> 55 rows, 1168 CTAs on 148 SMs).  ctas_per_sm is what the kernel's __launch_bounds__
-// guarantee: a grid sized for more CTAs than fit runs as one and a half waves.
-static int tall_tile_rows(const tl_chunk* c, int ctas_per_sm)
+// Stencil kernels: tall tiles (the two extra rows of the operand per tile are re-read from L2), sized so that the whole
+// grid is resident at once with some slack: about 6.75 tiles per SM (999 tiles on 148 SMs).  Measured in the resident
+// loop at 4000 x 4000 (profiles/pw_rows_r02.txt): 62-66 rows (992-1040 tiles) 0.2446-0.2450 ms per iteration, 55 rows
+// (1168 tiles, just under 8 per SM: round 1's choice) 0.2528, 48-52 rows 0.253 (0.29 on two ranks), 80 rows 0.2532.
+static int tall_tile_rows(const tl_chunk* c)
 {
     const int colb = (c->nx + TL_TILE_COLS - 1) / TL_TILE_COLS;
-    int rowblocks = (ctas_per_sm * 148) / colb;
+    int rowblocks = 999 / colb;
     if (rowblocks < 1) rowblocks = 1;
     int rows = (c->ny + rowblocks - 1) / rowblocks;
     if (rows < 8) rows = 8;
@@ -633,7 +633,7 @@ int tlk_tile_rows(const tl_chunk* c, int kernel)
     tune_from_env();
     if (g_rows[kernel] > 0) return g_rows[kernel];
     if (kernel == TUNE_UR || kernel == TUNE_P) return 8;
-    return tall_tile_rows(c, 8);
+    return tall_tile_rows(c);
 }
 dim3 tlk_hot_grid(const tl_chunk* c, int rows)
 {
@@ -1256,7 +1256,7 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
 // NORM: the kernel also returns sum r.r over the interior (all ranks), i.e. the calculate_2norm(r) that
 // cheby_driver.c:128-133 / ppcg_driver.c:136-141 run after it, without another pass over r.
 enum { MODE_CHEBY = 0, MODE_PPCG = 1 };
-#define TL_FS_CTAS_PER_SM 5 // 102 registers: the U = 2 load batch of five streams needs ~100
+#define TL_FS_CTAS_PER_SM 5 // register cap 102: the U = 2 load batch of five streams needs ~100
 template <int MODE, int U, bool MULTI, bool NORM>
 __global__ void __launch_bounds__(TL_TPB, TL_FS_CTAS_PER_SM)
 k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_out, double* __restrict__ f1,
@@ -1364,7 +1364,7 @@ static int launch_fused_stencil(tl_chunk* c, int mode, double alpha, double beta
 {
     const int field = (mode == MODE_CHEBY) ? TL_FIELD_U : TL_FIELD_SD;
     tune_from_env();
-    const int rows = g_rows[TUNE_W] > 0 ? g_rows[TUNE_W] : tall_tile_rows(c, TL_FS_CTAS_PER_SM);
+    const int rows = tlk_tile_rows(c, TUNE_W);
     dim3 grid = tlk_hot_grid(c, rows);
     TL_TRY(tlk_hot_check(c, grid));
     const int mask = tlk_external_mask(c);

@@ -101,10 +101,9 @@ enum { SUM_GENERIC = 0, SUM_HOT_W = 1, SUM_HOT_UR = 2, SUM_GENERIC_ALL = 3, SUM_
 static int gpu_tile_rows(int kind, int nx, int ny)
 {
     if (kind != SUM_HOT_W && kind != SUM_HOT_FS) return 8;
-    /* one balanced wave of tall tiles: 8 resident CTAs per SM for the CG matvec kernels, 5 for the one-pass
-     * Chebyshev / PPCG kernels (TL_FS_CTAS_PER_SM in tl_kernels.cu) */
+    /* tall tiles of the stencil kernels: about 6.75 tiles per SM (tall_tile_rows in tl_kernels.cu) */
     int colb = (nx + 255) / 256;
-    int rowblocks = ((kind == SUM_HOT_FS ? 5 : 8) * 148) / colb;
+    int rowblocks = 999 / colb;
     if (rowblocks < 1) rowblocks = 1;
     int rows = (ny + rowblocks - 1) / rowblocks;
     if (rows < 8) rows = 8;

@@ -154,3 +154,52 @@ def test_reduction_is_deterministic(setup):
     a = ch.run_cg_calc_w(0.0)
     b = ch.run_cg_calc_w(0.0)
     assert a == b
+
+
+def test_two_chunks_per_rank_accumulate_semantics():
+    """SURVEY.md 8b scalar-return convention with num_chunks_per_rank > 1: the drivers loop over the rank's chunks with
+    ONE accumulator; run_cg_init / run_cg_calc_w ADD their chunk's sum to it (cg.cpp:133,194), run_cg_calc_ur,
+    run_calculate_2norm, run_jacobi_iterate and run_field_summary ASSIGN (cg.cpp:253, solver_methods.cpp:116,
+    jacobi.cpp:116, field_summary.cpp:147-150), so the last chunk's value survives -- as in the reference."""
+    from exploringsycl_b200 import Chunk
+    chunks, fields = [], []
+    for n, (nx, ny) in enumerate([(70, 40), (33, 57)]):
+        ch = Chunk(nx, ny, HD, 100)
+        f = rng_fields(nx, ny, seed=100 + n)
+        upload(ch, f)
+        chunks.append(ch)
+        fields.append(f)
+    L = O.lib()
+    own_pw, own_rro, own_rrn = [], [], []
+    for ch, f in zip(chunks, fields):
+        x, y = ch.x, ch.y
+        o = dbl(); w = f["w"].copy()
+        L.orc_cg_calc_w(x, y, HD, f["p"], f["kx"], f["ky"], w, C.byref(o))
+        own_pw.append(o.value)
+    # cg_driver.c:72-85: pw = 0; for each chunk run_cg_calc_w(chunk, settings, &pw)
+    pw = 0.0
+    for ch in chunks:
+        pw = ch.run_cg_calc_w(pw)
+    assert rel(pw, own_pw[0] + own_pw[1]) < RED_TOL
+    # run_cg_calc_ur ASSIGNS: called with the same variable for both chunks, the second chunk's value is what is left
+    rrn = [ch.run_cg_calc_ur(0.37) for ch in chunks]
+    for ch, f, got in zip(chunks, fields, rrn):
+        x, y = ch.x, ch.y
+        u, r = f["u"].copy(), f["r"].copy()
+        w = f["w"].copy(); o = dbl()
+        L.orc_cg_calc_w(x, y, HD, f["p"], f["kx"], f["ky"], w, C.byref(o))
+        o2 = dbl()
+        L.orc_cg_calc_ur(x, y, HD, 0.37, f["p"], w, u, r, C.byref(o2))
+        assert rel(got, o2.value) < RED_TOL
+    # run_cg_init accumulates into *rro
+    rro = 0.125
+    for ch in chunks:
+        rro = ch.run_cg_init(1, 0.7, 1.3, rro)
+    exp = C.c_double(0.125)
+    for ch, f in zip(chunks, fields):
+        o = {k: f[k].copy() for k in ("u", "p", "r", "w", "kx", "ky")}
+        L.orc_cg_init(ch.x, ch.y, HD, 1, 0.7, 1.3, f["density"], f["energy"], o["u"], o["p"], o["r"], o["w"], o["kx"],
+                      o["ky"], C.byref(exp))
+    assert rel(rro, exp.value) < RED_TOL
+    for ch in chunks:
+        ch.close()
