@@ -103,6 +103,7 @@ extern "C" int tl_chunk_create(tl_chunk** out, int device, int nx, int ny, int h
         TL_CUDA(cudaHostGetDevicePointer((void**)&dptr, c->err_h, 0));
         TL_CUDA(cudaMemcpy((char*)c->scal + offsetof(DevScal, err_host), &dptr, sizeof(dptr), cudaMemcpyHostToDevice));
     }
+    TL_TRY(dev_zalloc(&c->colbuf, 2 * (size_t)g.y + 64));
     TL_TRY(dev_zalloc(&c->d_alphas, max_iters + 1));
     TL_TRY(dev_zalloc(&c->d_betas, max_iters + 1));
     // kernel_initialise.cpp:76-79: host coefficient arrays of max_iters doubles, zeroed
@@ -132,7 +133,7 @@ extern "C" int tl_chunk_destroy(tl_chunk* c)
     cudaFree(c->slab);
     cudaFree(c->cell_x); cudaFree(c->cell_y); cudaFree(c->vertex_x); cudaFree(c->vertex_y);
     cudaFree(c->partials); cudaFree(c->gpartials); cudaFree(c->gcount); cudaFree(c->scal); cudaFreeHost(c->scal_h); cudaFreeHost(c->err_h);
-    cudaFree(c->d_alphas); cudaFree(c->d_betas);
+    cudaFree(c->d_alphas); cudaFree(c->d_betas); cudaFree(c->colbuf);
     if (c->stamps) cudaFree(c->stamps);
     free(c->cg_alphas); free(c->cg_betas); free(c->cheby_alphas); free(c->cheby_betas);
     for (int fc = 0; fc < 4; ++fc) { cudaFree(c->face_send[fc]); cudaFree(c->face_recv[fc]); }

@@ -450,6 +450,8 @@ extern "C" int tl_comms_attach_chunk(tl_comms* k, tl_chunk* c)
     memset(&mc, 0, sizeof(mc));
     mc.num_ranks = k->num_ranks;
     mc.rank = k->rank;
+    mc.colbuf = c->colbuf;
+    mc.col_cap = c->g.y;
     double* tail = k->arena + arena_flags_off(k);
     mc.slots_local = (unsigned long long*)(tail + ARENA_SLOTS);
     mc.hflags_local = (unsigned long long*)(tail + ARENA_HFLAGS);

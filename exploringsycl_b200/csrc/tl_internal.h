@@ -87,6 +87,8 @@ struct MultiCtx {
                                   // calc_ur), the updated u / sd buffer (one-pass Chebyshev / PPCG kernels)
     unsigned long long* nb_hflag[4]; // neighbour's halo flag of the opposite face
     int nb_pitch[4], nb_x[4], nb_y[4], nb_off[4];
+    double* colbuf;               // local: [2][col_cap] parked left / right column cells (edge_remote_store<true>)
+    int col_cap;
 };
 
 struct tl_chunk {
@@ -104,6 +106,7 @@ struct tl_chunk {
     double* p2;                   // second p buffer of the fused p+w kernel (slab slot TL_SLAB_P2; P and P2 swap roles)
     double* alt[TL_NUM_FIELDS];   // second buffers of the one-pass Chebyshev (U) / PPCG (SD) kernels (slab slots
                                   // TL_SLAB_U2 / TL_SLAB_SD2; a field and its alternate swap roles every launch)
+    double* colbuf;               // device: 2 * g.y doubles, the resident loops' parked halo columns
     double* nb_slab[4];           // neighbours' slabs (peer-mapped), by my face; null if external or not attached
     size_t nb_field_elems[4];     // doubles per field inside that neighbour's slab
     double* partials;             // device, per-tile partial sums (4 lanes)

@@ -765,7 +765,7 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
 {
     DevScal* S = ra.S;
     double alpha = alpha_imm;
-    const HotTile t = hot_tile(g, rows, rev);
+    const HotTile t = hot_tile(g, rows, rev, MULTI && send_r_halo);
     const long pitch = g.pitch;
     double acc[1] = {0.0};
     long i = t.i;
@@ -819,15 +819,16 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
                     acc[0] += rv[q].x * rv[q].x;
                     if (t.v1) acc[0] += rv[q].y * rv[q].y;
                     if constexpr (MULTI) { // fused loop: the updated r edge cells go to the neighbours' halo of r
-                        if (send_r_halo) edge_remote_store(g, mc, mc.nb_f, jb + q, rv[q], t);
+                        if (send_r_halo) edge_remote_store<true>(g, mc, mc.nb_f, jb + q, rv[q], t);
                     }
                 }
             }
         }
     }
     if constexpr (MULTI) {
-        // only the tiles on a face with a neighbour made remote halo stores: visible system-wide before this CTA's ticket
-        if (send_r_halo && tile_sends_halo(g, mc, t)) __threadfence_system();
+        // only the tiles of the top / bottom row made remote halo stores (the columns are parked locally): visible
+        // system-wide before this CTA's ticket
+        if (send_r_halo && tile_sends_halo(g, mc, t, true)) __threadfence_system();
     }
     double tot[1];
     if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
@@ -838,10 +839,15 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
             // warp 0: sum_over_ranks(rrn), cg_driver.c:104, over NVLink; warp 1: fused loop, r's halo handshake (every CTA
             // fenced its halo stores before its ticket)
             if (threadIdx.x < 32) rrn = mc_allsum_warp(mc, 1, tot[0], S);
-            else if (send_r_halo && threadIdx.x < 64) {
-                mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x - 32);
-                __syncwarp();
-                if (threadIdx.x == 32) stamp(S, it, 1, 3);
+            else if (send_r_halo) { // warps 1-3: forward the parked columns, then warp 1 hand-shakes
+                forward_columns(g, mc, mc.nb_f, threadIdx.x - 32, TL_TPB - 32);
+                __threadfence_system();
+                asm volatile("bar.sync 2, %0;" ::"n"(TL_TPB - 32) : "memory");
+                if (threadIdx.x < 64) {
+                    mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x - 32);
+                    __syncwarp();
+                    if (threadIdx.x == 32) stamp(S, it, 1, 3);
+                }
             }
         }
         if (threadIdx.x != 0) return;
@@ -928,7 +934,7 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
 {
     constexpr bool multi = MULTI;
     double beta = beta_imm;
-    const HotTile t = hot_tile(g, rows, rev);
+    const HotTile t = hot_tile(g, rows, rev, MULTI);
     const long pitch = g.pitch;
     long i = t.i;
     int it = -1;
@@ -1333,7 +1339,7 @@ k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_o
                         if (t.v1) acc[0] += rn.y * rn.y;
                     }
                     if constexpr (MULTI) {
-                        if (sends) edge_remote_store(g, mc, mc.nb_f, jb + q, ao, t);
+                        if (sends) edge_remote_store<true>(g, mc, mc.nb_f, jb + q, ao, t);
                     }
                     am = ac; ac = an[q]; kyc = kyn[q]; al = aln[q]; ar = arn[q];
                 }
@@ -1341,7 +1347,7 @@ k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_o
         }
     }
     if constexpr (MULTI) {
-        if (tile_sends_halo(g, mc, t)) __threadfence_system(); // remote halo stores visible before this CTA's ticket
+        if (tile_sends_halo(g, mc, t, true)) __threadfence_system(); // remote row stores visible before this CTA's ticket
     }
     if constexpr (NORM) {
         double tot[1];
@@ -1349,13 +1355,22 @@ k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_o
             double nrm = tot[0];
             if constexpr (MULTI) {
                 if (threadIdx.x < 32) nrm = mc_allsum_warp(mc, 1, tot[0], ra.S); // sum_over_ranks, cheby_driver.c:132
-                else if (threadIdx.x < 64) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x - 32);
+                else { // warps 1-3: forward the parked columns, then warp 1 hand-shakes
+                    forward_columns(g, mc, mc.nb_f, threadIdx.x - 32, TL_TPB - 32);
+                    __threadfence_system();
+                    asm volatile("bar.sync 2, %0;" ::"n"(TL_TPB - 32) : "memory");
+                    if (threadIdx.x < 64) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x - 32);
+                }
             }
             if (threadIdx.x == 0) ra.S->sums[0] = nrm;
         }
     } else if constexpr (MULTI) {
-        if (grid_last_cta(ra.gcount, &ra.S->counter[1], t.tile, t.ntiles) && threadIdx.x < 32)
-            mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x);
+        if (grid_last_cta(ra.gcount, &ra.S->counter[1], t.tile, t.ntiles)) {
+            forward_columns(g, mc, mc.nb_f, threadIdx.x, TL_TPB);
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x < 32) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x);
+        }
     }
 }
 
