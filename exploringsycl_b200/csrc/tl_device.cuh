@@ -143,9 +143,15 @@ __device__ __forceinline__ void red_sync()
     if constexpr (CONSUMERS_ONLY) asm volatile("bar.sync 1, %0;" ::"n"(TL_TPB) : "memory");
     else __syncthreads();
 }
-template <int NR, bool CONSUMERS_ONLY = false>
+// `hook(group)` (optional) runs in every thread of the last CTA of each group once all tiles of that group are done
+// and their writes are visible -- the resident multi-rank kernels forward the group's parked halo columns there, while
+// the rest of the grid is still streaming.
+struct NoGroupHook {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+template <int NR, bool CONSUMERS_ONLY = false, class Hook = NoGroupHook>
 __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra, int tile, int ntiles,
-                                            double (&tot)[NR])
+                                            double (&tot)[NR], Hook hook = Hook())
 {
     __shared__ double sm[NR][TL_TPB / 32];
     __shared__ int s_flag;
@@ -172,6 +178,7 @@ __device__ __forceinline__ bool grid_reduce(double (&acc)[NR], const RedArgs& ra
     if (!s_flag) return false;
     // last CTA of this group: group sum (lanes of warps 0,1 hold one tile partial each)
     __threadfence();
+    hook(group);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         double v = 0.0;
@@ -314,24 +321,29 @@ __device__ __forceinline__ void mc_halo_handshake(const MultiCtx& mc, double* co
 // levels like grid_reduce so that thousands of CTAs do not queue on one address: tiles take a ticket of their group of
 // TL_RED_GROUP, the last tile of a group takes a ticket of the grid.  Every CTA calls it after its last store (remote
 // halo stores already fenced system-wide); returns true in every thread of the last CTA to arrive.
-__device__ __forceinline__ bool grid_last_cta(unsigned int* gcount, unsigned int* counter, int tile, int ntiles)
+template <class Hook>
+__device__ __forceinline__ bool grid_last_cta(unsigned int* gcount, unsigned int* counter, int tile, int ntiles, Hook hook)
 {
     __shared__ int s_last_cta;
+    const int group = tile / TL_RED_GROUP;
+    const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
+    const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int group = tile / TL_RED_GROUP;
-        const int ngroups = (ntiles + TL_RED_GROUP - 1) / TL_RED_GROUP;
-        const int gsize = min(TL_RED_GROUP, ntiles - group * TL_RED_GROUP);
-        int last = 0;
         __threadfence();
-        if (atomicAdd(&gcount[group], 1u) == (unsigned int)(gsize - 1)) {
-            gcount[group] = 0u;
-            __threadfence();
-            if (atomicAdd(counter, 1u) == (unsigned int)(ngroups - 1)) {
-                *counter = 0u;
-                last = 1;
-            }
-        }
+        s_last_cta = (atomicAdd(&gcount[group], 1u) == (unsigned int)(gsize - 1));
+    }
+    __syncthreads();
+    if (!s_last_cta) return false;
+    // last CTA of its group: every tile of the group is done
+    __threadfence();
+    hook(group);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        gcount[group] = 0u;
+        __threadfence();
+        const int last = (atomicAdd(counter, 1u) == (unsigned int)(ngroups - 1));
+        if (last) *counter = 0u;
         s_last_cta = last;
     }
     __syncthreads();
@@ -411,31 +423,41 @@ __device__ __forceinline__ void edge_remote_store(const Geo& g, const MultiCtx& 
     }
 }
 
-// Tail CTA (every tile of the grid has taken its ticket: the column buffer is complete): threads tid = 0 .. nthreads-1
-// copy the parked columns into the neighbours' halo columns.  The caller fences system-wide and synchronises the
-// forwarding threads before the per-face flags are released.
-__device__ __forceinline__ void forward_columns(const Geo& g, const MultiCtx& mc, double* const* nbf, int tid, int nthreads)
-{
-    for (int f = TL_FACE_LEFT; f <= TL_FACE_RIGHT; ++f) {
-        if (!nbf[f]) continue;
-        const double* src = mc.colbuf + (f == TL_FACE_LEFT ? 0 : mc.col_cap);
-        double* dst = nbf[f] + (long)mc.nb_off[f] + (f == TL_FACE_LEFT ? (mc.nb_x[f] - g.hd) : (g.hd - 1));
-        const long pitch = mc.nb_pitch[f];
-        for (int j0 = g.hd + tid; j0 < g.y - g.hd; j0 += 8 * nthreads) {
-            double v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int jj = j0 + q * nthreads;
-                if (jj < g.y - g.hd) v[q] = __ldcg(src + jj);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int jj = j0 + q * nthreads;
-                if (jj < g.y - g.hd) dst[(long)jj * pitch] = v[q];
+// Forwarding of the parked halo columns, group by group: run by every thread of the last CTA of tile group `group`
+// (TL_RED_GROUP consecutive tiles) once all tiles of the group are done.  The rows covered by the group's left-edge
+// (right-edge) tiles are copied from the local column buffer into the left (right) neighbour's halo column, and every
+// forwarding thread fences system-wide: the group's ticket of the grid-level count is taken after that, so when the
+// kernel's tail CTA releases the per-face flags every column cell has arrived.  Overlaps with the streaming of the rest
+// of the grid; the tail itself only hand-shakes.
+struct ForwardColumns {
+    const Geo& g;
+    const MultiCtx& mc;
+    int rows, gx, ntiles;
+    bool on;
+    __device__ __forceinline__ void operator()(int group) const
+    {
+        if (!on) return;
+        bool any = false;
+        for (int f = TL_FACE_LEFT; f <= TL_FACE_RIGHT; ++f) {
+            if (!mc.nb_f[f]) continue;
+            const int bxf = (f == TL_FACE_LEFT) ? 0 : gx - 1;
+            const int t_lo = group * TL_RED_GROUP, t_hi = min(t_lo + TL_RED_GROUP, ntiles); // tiles [t_lo, t_hi)
+            // tile-rows by with t_lo <= by * gx + bxf < t_hi
+            const int by_lo = (t_lo - bxf + gx - 1) / gx > 0 ? (t_lo - bxf + gx - 1) / gx : 0;
+            if (t_hi - 1 - bxf < 0) continue;
+            const int by_hi = (t_hi - 1 - bxf) / gx;
+            const int j_lo = g.hd + by_lo * rows, j_hi = min(g.hd + (by_hi + 1) * rows, g.y - g.hd);
+            const double* src = mc.colbuf + (f == TL_FACE_LEFT ? 0 : mc.col_cap);
+            double* dst = mc.nb_f[f] + (long)mc.nb_off[f] + (f == TL_FACE_LEFT ? (mc.nb_x[f] - g.hd) : (g.hd - 1));
+            const long pitch = mc.nb_pitch[f];
+            for (int jj = j_lo + (int)threadIdx.x; jj < j_hi; jj += TL_TPB) {
+                dst[(long)jj * pitch] = __ldcg(src + jj);
+                any = true;
             }
         }
+        if (any) __threadfence_system();
     }
-}
+};
 
 // Did this tile make remote halo stores, i.e. does it own cells on a face that has a neighbour?  (Those tiles fence
 // their stores system-wide before they take their end-of-kernel ticket.)  staged_cols: the columns went to the local

@@ -831,7 +831,8 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
         if (send_r_halo && tile_sends_halo(g, mc, t, true)) __threadfence_system();
     }
     double tot[1];
-    if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+    const ForwardColumns fwd{g, mc, rows, (int)gridDim.x, t.ntiles, MULTI && send_r_halo != 0};
+    if (grid_reduce<1, false>(acc, ra, t.tile, t.ntiles, tot, fwd)) {
         const int it = (mode == SCAL_DEV) ? sld(&S->iters) : -1;
         if (threadIdx.x == 0) stamp(S, it, 1, 1);
         double rrn = tot[0];
@@ -839,15 +840,10 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
             // warp 0: sum_over_ranks(rrn), cg_driver.c:104, over NVLink; warp 1: fused loop, r's halo handshake (every CTA
             // fenced its halo stores before its ticket)
             if (threadIdx.x < 32) rrn = mc_allsum_warp(mc, 1, tot[0], S);
-            else if (send_r_halo) { // warps 1-3: forward the parked columns, then warp 1 hand-shakes
-                forward_columns(g, mc, mc.nb_f, threadIdx.x - 32, TL_TPB - 32);
-                __threadfence_system();
-                asm volatile("bar.sync 2, %0;" ::"n"(TL_TPB - 32) : "memory");
-                if (threadIdx.x < 64) {
-                    mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x - 32);
-                    __syncwarp();
-                    if (threadIdx.x == 32) stamp(S, it, 1, 3);
-                }
+            else if (send_r_halo && threadIdx.x < 64) { // warp 1: every group has forwarded and fenced its columns
+                mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x - 32);
+                __syncwarp();
+                if (threadIdx.x == 32) stamp(S, it, 1, 3);
             }
         }
         if (threadIdx.x != 0) return;
@@ -992,7 +988,7 @@ k_cg_calc_p(Geo g, double* p, const double* r, DevScal* S, int mode, double beta
         // releases the neighbours' per-face flags and acquires its own: when this kernel completes, the halo of p that
         // the next matvec reads is in place (what halo_update_driver.c:22 provides in the reference).
         if (tile_sends_halo(g, mc, t)) __threadfence_system();
-        if (grid_last_cta(gcount, &S->counter[1], t.tile, t.ntiles) && threadIdx.x < 32) {
+        if (grid_last_cta(gcount, &S->counter[1], t.tile, t.ntiles, NoGroupHook()) && threadIdx.x < 32) {
             mc_halo_handshake(mc, mc.nb_f, S, threadIdx.x);
             __syncwarp();
             if (threadIdx.x == 0) stamp(S, it, 2, 3);
@@ -1349,28 +1345,20 @@ k_fused_stencil(Geo g, const double* __restrict__ a_in, double* __restrict__ a_o
     if constexpr (MULTI) {
         if (tile_sends_halo(g, mc, t, true)) __threadfence_system(); // remote row stores visible before this CTA's ticket
     }
+    const ForwardColumns fwd{g, mc, rows, (int)gridDim.x, t.ntiles, MULTI};
     if constexpr (NORM) {
         double tot[1];
-        if (grid_reduce<1>(acc, ra, t.tile, t.ntiles, tot)) {
+        if (grid_reduce<1, false>(acc, ra, t.tile, t.ntiles, tot, fwd)) {
             double nrm = tot[0];
             if constexpr (MULTI) {
                 if (threadIdx.x < 32) nrm = mc_allsum_warp(mc, 1, tot[0], ra.S); // sum_over_ranks, cheby_driver.c:132
-                else { // warps 1-3: forward the parked columns, then warp 1 hand-shakes
-                    forward_columns(g, mc, mc.nb_f, threadIdx.x - 32, TL_TPB - 32);
-                    __threadfence_system();
-                    asm volatile("bar.sync 2, %0;" ::"n"(TL_TPB - 32) : "memory");
-                    if (threadIdx.x < 64) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x - 32);
-                }
+                else if (threadIdx.x < 64) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x - 32);
             }
             if (threadIdx.x == 0) ra.S->sums[0] = nrm;
         }
     } else if constexpr (MULTI) {
-        if (grid_last_cta(ra.gcount, &ra.S->counter[1], t.tile, t.ntiles)) {
-            forward_columns(g, mc, mc.nb_f, threadIdx.x, TL_TPB);
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x < 32) mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x);
-        }
+        if (grid_last_cta(ra.gcount, &ra.S->counter[1], t.tile, t.ntiles, fwd) && threadIdx.x < 32)
+            mc_halo_handshake(mc, mc.nb_f, ra.S, threadIdx.x);
     }
 }
 
