@@ -41,7 +41,8 @@ struct DevScal {
     int p_pending;     // calc_ur ran: the matching calc_p must still run
     int max_iters;
     int conv_mode;     // 0: sqrt(|rrn|) < eps (cg_driver.c:24); 1: |rrn| < eps (cheby_driver.c:70)
-    int norm_every;    // resident Chebyshev loop: sample the 2-norm when (iteration + 1) % norm_every == 0
+    int sw_min_iters;  // CG pre-steps of the Chebyshev / PPCG drivers: stop once iters > sw_min_iters and rrn < sw_thresh
+    double sw_thresh;  // (the switch rule of cheby_driver.c:30-32 evaluated on the device); sw_min_iters < 0: off
     unsigned int counter[8]; // "last CTA done" tickets, one per reduction kernel family
     unsigned int pad;        // 0xdead: a peer wait timed out
     unsigned long long dbg[4]; // first timed-out wait: site, wanted value, seen value, block id

@@ -563,6 +563,8 @@ __global__ void k_reset_scal(DevScal* S, double eps, int max_iters)
     S->p_pending = 0;
     S->max_iters = max_iters;
     S->conv_mode = 0;
+    S->sw_min_iters = -1;
+    S->sw_thresh = 0.0;
     S->pad = 0u;
     S->dbg[0] = S->dbg[1] = S->dbg[2] = S->dbg[3] = 0ull;
     S->counter[0] = 0u;
@@ -857,6 +859,8 @@ k_cg_calc_ur(Geo g, double* u, double* r, const double* p, const double* w, doub
             S->iters = it + 1;
             S->p_pending = 1;
             if (conv_test(S, rrn) || it + 1 >= S->max_iters) S->conv = 1; // cg_driver.c:18,24; cheby_driver.c:70
+            // cheby_driver.c:30-32 / ppcg_driver.c:27-29: the rule that ends the CG pre-steps, seen from the iteration before
+            if (S->sw_min_iters >= 0 && it + 1 > S->sw_min_iters && rrn < S->sw_thresh) S->conv = 1;
             stamp(S, it, 1, 2);
         }
     }

@@ -114,11 +114,13 @@ static int cg_main_step_host(tl_chunk* c, tl_comms* k, int tt, double* rro, doub
 // (three kernels: p) or calc_ur (fused: r) stores its edge cells into the neighbours' halo and hand-shakes per face in
 // its tail.  No host round trip and no separate halo / all-reduce launches inside the loop; the host only polls the
 // convergence flag once per batch.
-__global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test)
+__global__ void k_set_stop(DevScal* S, int stop_iters, double eps, int abs_test, int sw_min_iters, double sw_thresh)
 {
     S->max_iters = stop_iters;
     S->eps = eps;
     S->conv_mode = abs_test;
+    S->sw_min_iters = sw_min_iters;
+    S->sw_thresh = sw_thresh;
     S->conv = (S->iters >= stop_iters) ? 1 : 0;
 }
 
@@ -133,12 +135,15 @@ static bool use_pdl()
     return v == 1;
 }
 
+// sw_min_iters >= 0: additionally stop after the first iteration that leaves iters > sw_min_iters and rrn < sw_thresh
+// (the CG pre-steps of the Chebyshev / PPCG drivers end there; decided on the device from the global rrn, so every rank
+// stops at the same iteration and the host never has to step the loop one iteration at a time).
 static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double eps, int abs_test, int batch,
-                               long* launches, bool fused = false)
+                               long* launches, bool fused = false, int sw_min_iters = -1, double sw_thresh = 0.0)
 {
     const bool pdl = use_pdl();
     const bool multi = k && tl_comms_size(k) > 1 && c->has_peers;
-    k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test);
+    k_set_stop<<<1, 1, 0, c->stream>>>(c->scal, stop_iters, eps, abs_test, sw_min_iters, sw_thresh);
     ++g_tl_launches;
     if (batch <= 0) batch = 32;
     // Two pinned status snapshots in flight: batch b+1 is enqueued before batch b's status is read,
@@ -226,17 +231,13 @@ static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double 
 }
 
 // Which form of the resident CG iteration runs for this chunk and option value (same answer on every rank of a
-// decomposition; results are bit-identical either way):
-//   one rank                      fused (calc_pw + calc_ur) unless fuse_p_into_w == 0
-//   several ranks, option 2       fused, r's halo travels
-//   several ranks, option 1 auto  fused when the decomposition has no left/right neighbours (1 x N: measured +2.5 % at
-//                                 N = 2); with left/right neighbours the three-kernel form was faster (+6 % at 2 x 4)
+// decomposition; results are bit-identical either way): fused (calc_pw + calc_ur, 96 B/cell moved) unless
+// fuse_p_into_w == 0.  Round 1 fell back to three kernels on decompositions with left/right neighbours; with the
+// halo columns parked and forwarded group by group the fused form wins there too (profiles/multi_rank_stamps_r02.txt:
+// 2 x 2 ranks 0.262 vs 0.299 ms per iteration, 2 x 4 ranks 0.265 vs 0.301).
 extern "C" int tl_cg_loop_is_fused(const tl_chunk* c, int fuse_p_into_w)
 {
-    if (!c || fuse_p_into_w == 0) return 0;
-    if (!c->has_peers) return 1;
-    const bool lr_nb = c->nb[TL_FACE_LEFT] != TL_EXTERNAL_FACE || c->nb[TL_FACE_RIGHT] != TL_EXTERNAL_FACE;
-    return (fuse_p_into_w == 2 || !lr_nb) ? 1 : 0;
+    return (c && fuse_p_into_w != 0) ? 1 : 0;
 }
 
 static bool use_resident_multi(const tl_chunk* c, tl_comms* k)
@@ -406,28 +407,19 @@ static int cg_presteps(tl_chunk* c, tl_comms* k, const tl_solve_opts* o, int* fi
     int tt = 0;
     *ended = false;
     const bool resident = !multi || use_resident_multi(c, k);
-    auto iterate = [&](int stop, int bt) {
-        return cg_iterate_resident(c, multi ? k : nullptr, stop, o->eps, 1, bt, launches);
-    };
     if (resident) {
-        // The rule cannot fire before tt = presteps+1 (or 21 with error_switch): run that many
-        // resident iterations (with the |error| < eps end test of cheby_driver.c:70 active on the
-        // device), then one at a time while the rule still says "CG".
-        int first = o->error_switch ? 21 : o->presteps + 1;
-        if (first > o->max_iters) first = o->max_iters;
-        TL_TRY(iterate(first, o->batch));
+        // One resident call: the |error| < eps end test of cheby_driver.c:70 AND the switch rule (tt > presteps &&
+        // error < 1, or with errswitch error < eps_lim && tt > 20: cheby_driver.c:30-32) are evaluated on the device after
+        // every iteration, so the loop stops exactly where the reference's loop index would leave CG.
+        const bool fused = tl_cg_loop_is_fused(c, o->fuse_p_into_w) != 0;
+        TL_TRY(cg_iterate_resident(c, multi ? k : nullptr, o->max_iters, o->eps, 1, o->batch, launches, fused,
+                                   o->error_switch ? 20 : o->presteps, o->error_switch ? o->eps_lim : 1.0));
         *error = c->scal_h->error;
         if (fabs(*error) < o->eps) {
             *ended = true;
             tt = c->scal_h->iters - 1;
         } else {
             tt = c->scal_h->iters;
-            while (tt < o->max_iters && !switch_rule(o, 0, tt, *error)) {
-                TL_TRY(iterate(tt + 1, 1));
-                *error = c->scal_h->error;
-                if (fabs(*error) < o->eps) { *ended = true; break; }
-                tt = c->scal_h->iters;
-            }
         }
         TL_TRY(fetch_cg_coeffs(c, c->scal_h->iters));
         // u and p halos as after halo_update_driver of the last CG iteration (cheby_driver.c:68)
