@@ -24,7 +24,13 @@ parity  = BEFORE anything is timed: a 250x250 deck decomposed over the N ranks (
           FAILS otherwise.  (The oracle is the checker here, never the thing measured.)
 roofline= dominant kernel of the iteration (cg_calc_pw or cg_calc_ur, 48 B/cell each) timed live with CUDA events on
           the launching stream vs MEASURED_PEAKS.json; traffic = DRAM bytes per launch of that kernel from the
-          committed ncu capture (profiles/traffic.json; null when the capture does not cover the kernel)
+          committed ncu capture (profiles/traffic.json; null when the capture does not cover the kernel); in_loop = the
+          same kernel's duration inside the resident loop, from the device stamps of iteration_profile
+iteration_profile = where an iteration's time goes: %globaltimer stamps taken by the loop kernels themselves (body,
+          NVLink all-gather of the partial sums, halo hand-shake, launch gap), median over 300 iterations, min / max over
+          the ranks
+loop_form_tuning = (N >= 4) the two bit-identical forms of the CG iteration (fused two-kernel / three-kernel) timed on a
+          capped solve before the timed region; the faster one runs
 extra   = (N > 1) the other named configs of BASELINE.json, device-timed the same way with the iteration count capped:
           strong scaling of 4000x4000 over the N GPUs; at N = 8 also CG 16000^2 and 32000^2 and Chebyshev / PPCG 8000^2
 cpu_baseline / --impl reference = the CPU oracle (C + OpenMP restatement of the reference kernels and
@@ -367,9 +373,17 @@ def main():
             traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
         except Exception:
             traffic = None
+    in_loop = None
+    if iteration_profile and (dom_name + ".body") in iteration_profile:
+        b = iteration_profile[dom_name + ".body"]
+        us = b["max"] if isinstance(b, dict) else b
+        if us > 0:
+            in_loop = {"us": us, "gb_s": chunk_cells * dom["bytes_per_cell"] / us / 1e3,
+                       "frac": chunk_cells * dom["bytes_per_cell"] / us / 1e3 / peak,
+                       "how": "device %globaltimer stamps inside the resident loop (slowest rank)"}
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["gb_s"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": chunk_cells * dom["bytes_per_cell"], "kernels": kern,
+                "algorithmic_bytes_per_launch": chunk_cells * dom["bytes_per_cell"], "kernels": kern, "in_loop": in_loop,
                 "solve_gb_s_104B": value / n_gpus * BYTES_PER_CELL_ITER / 1e9,
                 "solve_frac_104B": value / n_gpus * BYTES_PER_CELL_ITER / 1e9 / peak}
     decomposition = app.decomposition
@@ -384,9 +398,11 @@ def main():
         cases = [("cg_4000_strong", 4000, 4000, "cg", 1000)]
         if world == 8:
             cases += [("cg_16000", 16000, 16000, "cg", 400), ("cg_32000", 32000, 32000, "cg", 200),
-                      # Chebyshev / PPCG run to convergence: the CG pre-steps only hand over once the residual has
-                      # dropped below 1 (cheby_driver.c:30-32), thousands of iterations into the solve at this size
-                      ("cheby_8000", 8000, 8000, "cheby", 30000), ("ppcg_8000", 8000, 8000, "ppcg", 30000)]
+                      # The CG pre-steps only hand over once the residual has dropped below 1 (cheby_driver.c:30-32): ~1900
+                      # iterations into the solve at this size (profiles/cheby_ppcg_r02.txt).  The caps leave ~2100
+                      # Chebyshev iterations / ~600 PPCG outer steps (6000 inner steps) in the timed solve; run to
+                      # convergence the same solves take 30000+ iterations (6 s Chebyshev, 33 s PPCG per timestep).
+                      ("cheby_8000", 8000, 8000, "cheby", 4000), ("ppcg_8000", 8000, 8000, "ppcg", 2500)]
         for name, ex, ey, solver, cap in cases:
             try:
                 r = timed_case(ex, ey, solver, cap, 2 if solver == "cg" else 1, 1, fuse_env)

@@ -1208,7 +1208,8 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
     const int rows = tlk_tile_rows(c, TUNE_PW);
     dim3 grid = tlk_hot_grid(c, rows);
     TL_TRY(tlk_hot_check(c, grid));
-    if (tlk_pw_uses_bulk()) { // optional: TMA bulk-copy row pipeline, persistent CTAs (tl_bulk.cu); bit-identical results
+    // optional: TMA bulk-copy row pipeline, persistent CTAs (tl_bulk.cu); bit-identical results; one rank only
+    if (tlk_pw_uses_bulk() && !(mc && mc->num_ranks > 1)) {
         TL_TRY(tlk_cg_calc_pw_bulk(c, rev, mc, rows, pdl));
         double* tmp = c->f[TL_FIELD_P];
         c->f[TL_FIELD_P] = c->p2;

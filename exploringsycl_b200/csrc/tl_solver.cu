@@ -164,9 +164,7 @@ static int cg_iterate_resident(tl_chunk* c, tl_comms* k, int stop_iters, double 
     }
     int nb = 0, n_pw = 0;
     bool done = (enq >= stop_iters);
-    // TL_DBG_NOSEND=1 (timing experiments only, WRONG results): the fused loop keeps r's halo at home
-    static const bool dbg_nosend = getenv("TL_DBG_NOSEND") && getenv("TL_DBG_NOSEND")[0] == '1';
-    const bool send_r = multi && !dbg_nosend;
+    const bool send_r = multi; // fused loop on several ranks: calc_ur delivers r's halo to the neighbours
     while (!done) {
         const int todo = (stop_iters - enq) < batch ? (stop_iters - enq) : batch;
         for (int it = 0; it < todo; ++it) {

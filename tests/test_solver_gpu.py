@@ -170,6 +170,30 @@ def test_fused_p_into_w_is_bit_identical(mesh):
         assert np.array_equal(a[hd - 1:-(hd - 1), hd - 1:-(hd - 1)], b[hd - 1:-(hd - 1), hd - 1:-(hd - 1)]), f
 
 
+@pytest.mark.parametrize("stages", [3, 4, 8])
+def test_tma_row_pipeline_variant_is_bit_identical(stages):
+    """tl_set_pw_pipeline(1, ..): the fused p+w kernel on a cp.async.bulk / mbarrier shared-memory row pipeline with
+    persistent CTAs (tl_bulk.cu) must give the register kernel's results bit for bit (fields, counts, residuals)."""
+    from exploringsycl_b200 import Settings, TeaLeaf, lib, read_config
+    L = lib()
+    res = []
+    try:
+        for mode in (0, 1):
+            assert L.tl_set_pw_pipeline(mode, stages, 0) == 0
+            s, states = read_config(os.path.join(DECKS, "tea_250_cg.in"), Settings(grid_x_cells=301, grid_y_cells=157))
+            s.end_step = 2
+            app = TeaLeaf(s, states)
+            summary = app.diffuse()
+            res.append((summary, [(h["iters_a"], h["error"]) for h in app.history],
+                        {f: app.chunk.read(f)[2:-2, 2:-2] for f in (3, 7, 8, 2)}))
+            app.close()
+    finally:
+        L.tl_set_pw_pipeline(0, 4, 0)
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    for f in res[0][2]:
+        assert np.array_equal(res[0][2][f], res[1][2][f]), f
+
+
 @pytest.mark.parametrize("rows,batch", [(8, 1), (16, 4), (32, 2)])
 def test_tuning_does_not_change_fields(rows, batch):
     """Load-batch depth never changes results; rows per tile only reorders the reduction."""

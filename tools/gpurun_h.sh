@@ -12,6 +12,7 @@ timeout 300 python tools/stamps.py --tag n1_fused > $S 2>&1
 timeout 300 python tools/stamps.py --tag n1_three --fused 0 >> $S 2>&1
 timeout 300 $TR --master-port 29531 tools/stamps.py --tag n2_fused --fused 2 >> $S 2>&1
 timeout 300 $TR --master-port 29532 tools/stamps.py --tag n2_three --fused 0 >> $S 2>&1
+# (TL_DBG_NOSEND was a timing-only diagnostic switch of this call; removed from the library afterwards)
 TL_DBG_NOSEND=1 timeout 300 $TR --master-port 29533 tools/stamps.py --tag n2_fused_NOSEND_diagnostic --fused 2 >> $S 2>&1
 TL_PDL=0 timeout 300 $TR --master-port 29534 tools/stamps.py --tag n2_fused_nopdl --fused 2 >> $S 2>&1
 grep "^#\|^  [0-9]" $S
