@@ -93,9 +93,12 @@ def stress_worker(rank, world, session, grid, reps, skew, out):
 def deck_worker(rank, world, session, deck_file, over, out, skew=None):
     if skew:
         os.environ["TL_TEST_SKEW"] = skew
-    from exploringsycl_b200 import Comms, TeaLeaf, read_config
+    from exploringsycl_b200 import Comms, Settings, TeaLeaf, read_config
     comms = Comms(session, rank, world, device=rank)
-    s, states = read_config(os.path.join(DECKS, deck_file))
+    over = dict(over)
+    # a mesh override goes in BEFORE the deck is parsed (dx, dy and the states' shrunk extents derive from it)
+    preset = Settings(grid_x_cells=over.pop("grid_x_cells", 10), grid_y_cells=over.pop("grid_y_cells", 10))
+    s, states = read_config(os.path.join(DECKS, deck_file), preset)
     for k, v in over.items():
         setattr(s, k, v)
     app = TeaLeaf(s, states, comms, device=rank)
@@ -238,3 +241,21 @@ def test_decomposed_cg_is_bit_identical_to_the_oracle_n_chunk_run(world, fused):
         assert [h["iters_a"] for h in hist] == ores["iters_a"]
         assert [h["error"] for h in hist] == ores["error"]
         assert [summary[k] for k in ("vol", "mass", "ie", "temp")] == [ores[k] for k in ("vol", "mass", "ie", "temp")]
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_wide_chunks_with_unaligned_tile_groups_are_bit_identical_to_the_oracle(world):
+    """1200 x 600 cells: every chunk is several column tiles wide (3 at world 4), so the 64-tile groups of the grid
+    reduction straddle tile rows and the group-wise forwarding of the parked halo columns (ForwardColumns,
+    tl_device.cuh) has to work out which rows of the left / right edge tiles each group owns.  Fused and three-kernel
+    loops against the oracle's N-chunk run, bit for bit."""
+    if ngpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    over = {"end_step": 2, "grid_x_cells": 1200, "grid_y_cells": 600}
+    ores = O.run_deck(O.make_deck(1200, 600, end_step=2, num_chunks=world), gpu_sum_order=True)
+    for fused in (2, 0):
+        res = launch(deck_worker, world, ("tea_250_cg.in", dict(over, fuse_p_into_w=fused)))
+        for rank, summary, hist in res:
+            assert [h["iters_a"] for h in hist] == ores["iters_a"], (fused, rank)
+            assert [h["error"] for h in hist] == ores["error"], (fused, rank)
+            assert [summary[k] for k in ("vol", "mass", "ie", "temp")] == [ores[k] for k in ("vol", "mass", "ie", "temp")]
