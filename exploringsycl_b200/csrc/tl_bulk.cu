@@ -18,9 +18,9 @@
 //     updated p from the adjacent lanes by shuffle (the two edge lanes of a warp read them from the staged row instead
 //     of issuing scalar global loads), slide rows j-1, j, j+1 through registers and store w and p with 128-bit stores.
 //
-// Multi-rank (MULTI): head and tail are k_cg_calc_pw's -- the neighbours' halo of r is in place when the preceding
-// calc_ur completes (its tail CTA acquires the halo flags; bulk copies read through L2, the point of coherence for
-// NVLink peer stores, and never allocate in L1), and the tail CTA combines the ranks' p.w partials.
+// One rank only: the multi-rank resident loop always runs the register kernel (tlk_cg_calc_pw); the MULTI parameter
+// of this kernel is kept so that its body stays line for line comparable with k_cg_calc_pw, but only MULTI = false is
+// instantiated.
 //
 // STATUS (round 2, measured on B200, profiles/pw_pipeline_r02.txt): bit-identical to the register-staged kernel on
 // every mesh tried, and exactly as fast under ncu (126.2 us vs 126.1 us at 4000^2, 749 MB of DRAM traffic and 72 % DRAM
@@ -368,11 +368,13 @@ int tlk_cg_calc_pw_bulk(tl_chunk* c, bool rev, const MultiCtx* mc, int rows, boo
 {
     dim3 tiles = tlk_hot_grid(c, rows);
     TL_TRY(tlk_hot_check(c, tiles));
-    const bool multi = mc && mc->num_ranks > 1;
+    if (mc && mc->num_ranks > 1) {
+        tl_set_error("the bulk-copy calc_pw pipeline runs on one rank only");
+        return TL_ERR_ARG;
+    }
 #define PW_CASE(S)                                                            \
     case S:                                                                   \
-        TL_TRY(multi ? (launch_pw<S, true>(c, rev, mc, rows, tiles, pdl))     \
-                     : (launch_pw<S, false>(c, rev, mc, rows, tiles, pdl)));  \
+        TL_TRY((launch_pw<S, false>(c, rev, mc, rows, tiles, pdl)));          \
         break
     switch (g_pw_stages) {
         PW_CASE(3);

@@ -99,12 +99,14 @@ __device__ __forceinline__ void spin_flag(const unsigned long long* flag, unsign
         __nanosleep(64);
     }
 }
-// Loads of fields that change inside the solver loop (p, r, u, w).  ld.global.cg is served by L2, the point of
-// coherence both for NVLink peer stores (halo cells of p / r written by the neighbours while this kernel runs) and for the
-// preceding kernel of a programmatic dependent launch: with PDL this kernel's CTAs share SMs with the still-draining
-// predecessor and no launch boundary has invalidated L1, so the non-coherent path (ld.global.nc) or an L1 hit could
-// return a line from two launches ago.  The hot kernels therefore read those fields with COH = true; the constant
-// coefficient fields kx, ky keep the read-only path.
+// Loads of fields that change inside the solver loop (p, r, u, w).  COH = true: ld.global.cg, served by L2 and never
+// allocating in L1.  The streaming kernels use it throughout -- every byte is used once, so L1 brings nothing, and
+// the rows they request BEFORE griddepcontrol.wait (programmatic dependent launch: the CTA is resident while the
+// predecessor drains) must not leave lines in L1 that a later launch could hit.  After the wait a kernel may use the
+// default L1-allocating loads for data nobody writes while it runs (cg_calc_w does, for its neighbour cells): the wait
+// makes the predecessors' writes visible, and on several ranks the neighbours' halo stores belong to the predecessor,
+// whose tail CTA hand-shook before it completed.  COH = false: the read-only path (ld.global.nc) of the constant
+// coefficient fields kx, ky.
 template <bool COH>
 __device__ __forceinline__ double2 ldp2(const double* p)
 {

@@ -126,7 +126,7 @@ struct tl_chunk {
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
     tl_comms* comms;              // non-null once attached
-    MultiCtx mc;                  // template filled by tl_comms_attach_chunk (tl/it_global/sbase/hbase per launch)
+    MultiCtx mc;                  // template filled by tl_comms_attach_chunk (tl / sbase / hbase / nb_f are set per launch)
     double* nb_recv[4];           // neighbours' receive buffers of the generic halo exchange (peer-mapped)
     unsigned long long* nb_flag[4];
     unsigned long long* nb_ack[4];   // neighbour's "buffer consumed" flag for what it SENDS to my face f (I release it)
