@@ -12,9 +12,8 @@ Reported per rank, median over the iterations (first 5 dropped), in microseconds
                      the others (every clock is per GPU, so only same-rank differences are used)
   halo   = t3 - t1   halo hand-shake (kernels that send a halo)
   gap    = next kernel's t0 - this kernel's last stamp: launch / dependency-resolution latency between kernels
-and the whole iteration (t0 of the matvec to t0 of the next matvec).  One JSON line per run goes to
-gpurun_out/stamps_<tag>.json (rank 0 gathers the ranks' tables through the comms layer's host mailboxes: none needed --
-each rank writes its own file, rank 0 merges after a barrier).
+and the whole iteration (t0 of the matvec to t0 of the next matvec).  Every rank writes gpurun_out/stamps_<tag>_r<rank>.json;
+after a barrier rank 0 merges them into gpurun_out/stamps_<tag>.json and prints the table.
 """
 import argparse
 import ctypes as C
