@@ -79,7 +79,7 @@ class Settings:  # settings.h:64-123 with the defaults of settings.h:15-45
     profiler_on: bool = False   # deck key the reference ignores (read_config_clean)
     deck_warnings: List[str] = dc_field(default_factory=list)
     batch: int = 0
-    fuse_p_into_w: int = 1  # 0: reference kernel sequence; 1: auto; 2: always fused (bit-identical), see tl_solve_opts
+    fuse_p_into_w: int = 1  # 0: the reference's kernel sequence; non-zero: fused / one-pass kernels (bit-identical), see tl_solve_opts
 
     def reset_fields_to_exchange(self):  # settings.c:64-70
         self.fields_to_exchange = [False] * NUM_FIELDS

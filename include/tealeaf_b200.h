@@ -250,7 +250,7 @@ void tl_host_free_pinned(void* p);
  * one hot kernel on the chunk's stream and returns the average CUDA-event milliseconds per launch.
  * which: 0 cg_calc_w, 1 cg_calc_ur, 2 cg_calc_p, 3 fused p+w (overwrites p, w and the solver scalars),
  * 4 cheby_iterate, 5 cheby_calc_u, 6 ppcg_calc_ur, 7 ppcg_calc_sd, 8 jacobi_iterate (copy + iterate),
- * 9 calculate_residual, 10 calculate_2norm, 11 field_summary, 12 cg_init (3 kernels), 13 finalise,
+ * 9 calculate_residual, 10 calculate_2norm, 11 field_summary, 12 cg_init (one pass), 13 finalise,
  * 14 copy_u, 15 cheby_init, 16 fused cheby iteration, 17 fused ppcg inner iteration.
  * The timed kernels overwrite solver fields. */
 int tl_time_kernel(tl_chunk* c, int which, int reps, double* ms_per_launch);
