@@ -590,6 +590,7 @@ int tlk_reset_solve_scalars(tl_chunk* c, double eps, int max_iters)
 // re-read from L2), the streaming kernels want many small tiles (better tail balance).
 static int g_rows[4] = {0, 0, 0, 0};
 static int g_batch[4] = {2, 4, 4, 1};
+static bool g_batch_user[4] = {false, false, false, false}; // set through tl_set_tuning: no heuristic on top
 extern "C" int tl_set_tuning(int kernel, int rows, int batch)
 {
     if (kernel < 0 || kernel > 3 || rows < 0 || rows > 256 || (batch != 1 && batch != 2 && batch != 4)) {
@@ -598,6 +599,7 @@ extern "C" int tl_set_tuning(int kernel, int rows, int batch)
     }
     g_rows[kernel] = rows;
     g_batch[kernel] = batch;
+    g_batch_user[kernel] = true;
     return TL_OK;
 }
 // TL_TUNE="kernel:rows:batch,..." (e.g. "1:16:4,2:16:4") overrides the defaults at first use: experiments only.
@@ -1227,7 +1229,13 @@ int tlk_cg_calc_pw(tl_chunk* c, bool rev, const MultiCtx* mc, bool pdl)
         TL_CUDA(tl_launch(k_cg_calc_pw<U, false>, grid, dim3(TL_TPB), 0, c->stream, pdl, c->g, c->f[TL_FIELD_P],  \
                           c->p2, c->f[TL_FIELD_R], c->f[TL_FIELD_KX], c->f[TL_FIELD_KY], c->f[TL_FIELD_W],        \
                           c->d_alphas, c->d_betas, ra, rows, rev ? 1 : 0, mask, g_single_ctx))
-    switch (g_batch[TUNE_PW]) {
+    // Load batch: one row at a time for tall tiles (4000 x 4000: 65 rows; a batch of 2 costs occupancy and is 2-10 %
+    // slower there), two rows for the short tiles of small, L2-resident chunks, where the row-to-row dependent latency
+    // is what a tile's time consists of (2000 x 1000: 9 rows, 40.2 -> 37.6 us per iteration; 1000 x 1000: 28.0 -> 25.0;
+    // profiles/pw_rows_r02.txt).  Results do not depend on the batch.
+    int batch = g_batch[TUNE_PW];
+    if (!g_batch_user[TUNE_PW] && rows <= 16) batch = 2;
+    switch (batch) {
     case 1: LAUNCH_PW(1); break;
     case 2: LAUNCH_PW(2); break;
     default: LAUNCH_PW(4); break;

@@ -12,7 +12,11 @@ rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE",
 local = int(os.environ.get("LOCAL_RANK", "0"))
 L = lib()
 nx, ny = WEAK[world]
-specs = sys.argv[1:] or ["0:1"]
+argv = sys.argv[1:]
+if argv and argv[0] == "--cells":  # --cells X Y : another mesh than the weak-scaling one
+    nx, ny = int(argv[1]), int(argv[2])
+    argv = argv[3:]
+specs = argv or ["0:1"]
 for n_, spec in enumerate(specs):
     rows, batch = (int(v) for v in spec.split(":"))
     L.tl_set_tuning(3, rows, batch)
@@ -27,8 +31,8 @@ for n_, spec in enumerate(specs):
         ms = info.gpu_ms / info.total_iters
         best = ms if best is None or ms < best else best
     if rank == 0:
-        print("ranks=%d calc_pw rows=%3d batch=%d  loop %.4f ms/iter  %.4e cell-iter/s" % (
-            world, rows, batch, best, nx * ny / best * 1e3), flush=True)
+        print("ranks=%d mesh %dx%d calc_pw rows=%3d batch=%d  loop %.4f ms/iter  %.4e cell-iter/s" % (
+            world, nx, ny, rows, batch, best, nx * ny / best * 1e3), flush=True)
     app.close()
     if comms:
         comms.finalise()
